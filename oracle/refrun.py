@@ -96,6 +96,8 @@ def run(frames, method, rejection=NO_REJEC, normalize=NO_NORM, sig=(0.0, 0.0),
     with _quiet_stdout(not verbose):
         rv = lib().oref_run(C.byref(cfg), out.ctypes.data, irej.ctypes.data,
                             None if coeff is None else coeff.ctypes.data, timing.ctypes.data)
+    if coeff is not None and normalize == NO_NORM:
+        coeff[0], coeff[1], coeff[2] = 0.0, 1.0, 1.0     # compute_normalization's defaults (stacking.c:130-134)
     return dict(out=out, irej=irej.reshape(3, 2), coeff=coeff, retval=rv,
                 t_method=float(timing[0]), t_norm=float(timing[1]))
 

@@ -1,0 +1,82 @@
+// ssc_device.cuh -- device-side primitives shared by the stacking kernels.
+//
+// Every floating-point expression that mirrors the reference's double
+// arithmetic is spelled with the round-to-nearest intrinsics (__dadd_rn,
+// __dmul_rn, __ddiv_rn, __dsqrt_rn): they are never contracted into FMAs, so
+// each operation is rounded individually exactly as the reference's x86-64
+// build (gcc -O2, no -mfma, configure.ac:38-48) rounds it.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/siril_stack_cuda.h"
+
+namespace ssc {
+
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+
+// round_to_WORD, src/core/utils.c:68-74
+__device__ __forceinline__ unsigned int round_to_word(double x) {
+	if (x <= 0.0) return 0u;
+	if (x > 65535.0) return 65535u;
+	return (unsigned int) __double2int_rz(dadd(x, 0.5));
+}
+
+// Normalization of one raw sample.
+// mean path: stacking.c:1635-1652 (NO_NORM copies the sample);
+// median path: stacking.c:750-764 (always through double; identical results).
+__device__ __forceinline__ unsigned int normalize_sample(unsigned int p, int mode, double offset,
+		double mul, double scale) {
+	switch (mode) {
+	case ADDITIVE:
+	case ADDITIVE_SCALING:
+		return round_to_word(dsub(dmul((double) (int) p, scale), offset));
+	case MULTIPLICATIVE:
+	case MULTIPLICATIVE_SCALING:
+		return round_to_word(dmul(dmul((double) (int) p, scale), mul));
+	default:
+		return p;
+	}
+}
+
+// gsl_stats_ushort_sd (stacking.c:1676,1698,1713,1727) from exact integer sums:
+// n*Q - S*S is an exact integer below 2^64 for n <= 65536, so the biased
+// variance carries a single rounding; then the reference's own
+// sqrt(variance * (n / (n-1))).  GSL accumulates the same quantity in x87
+// long double, which FP64 cannot reproduce bit for bit.
+__device__ __forceinline__ double sd_from_sums(unsigned long long S, unsigned long long Q, int n) {
+	unsigned long long D = (unsigned long long) n * Q - S * S;
+	double var = ddiv(__ull2double_rn(D), (double) ((long long) n * n));
+	return dsqrt(dmul(var, ddiv((double) n, (double) (n - 1))));
+}
+
+// sigma_clipping, stacking.c:1148-1161: -1 low, +1 high, 0 keep
+__device__ __forceinline__ int clip_sigma(unsigned int p, double slow, double shigh, double sigma,
+		double median) {
+	double x = (double) (int) p;
+	if (dsub(median, x) > dmul(slow, sigma)) return -1;
+	if (dsub(x, median) > dmul(shigh, sigma)) return 1;
+	return 0;
+}
+
+// percentile_clipping, stacking.c:1130-1143
+__device__ __forceinline__ int clip_percentile(unsigned int p, double plow, double phigh, double median) {
+	double x = (double) (int) p;
+	if (ddiv(dsub(median, x), median) > plow) return -1;
+	if (ddiv(dsub(x, median), median) > phigh) return 1;
+	return 0;
+}
+
+// line_clipping, stacking.c:1170-1183
+__device__ __forceinline__ int clip_line(unsigned int p, double slow, double shigh, double sigma, int i,
+		double a, double b) {
+	double x = (double) (int) p, xi = (double) i;
+	if (ddiv(dsub(dadd(dmul(a, xi), b), x), sigma) > slow) return -1;
+	if (ddiv(dsub(dsub(x, dmul(a, xi)), b), sigma) > shigh) return 1;
+	return 0;
+}
+
+}  // namespace ssc

@@ -1,0 +1,42 @@
+// ssc_kernels.h -- host-callable launchers of the CUDA kernels (internal; the
+// public surface is include/siril_stack_cuda.h).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/siril_stack_cuda.h"
+
+#define SSC_GENERIC_MAX_FRAMES 2048
+
+namespace ssc {
+
+struct StackParams {
+	ssc_band band;
+	int normalize;
+	const double *coeff;		// device double[3][N] or nullptr
+	int rejection;
+	double sig_low, sig_high;
+	WORD *out;
+	size_t out_layer_stride;
+	int out_buf_row0;
+	unsigned long long *counters;	// device uint64[SSC_COUNTERS] or nullptr
+};
+
+// ssc_stack_generic.cu
+int launch_stack_generic(const StackParams &p, const unsigned int *list, const unsigned int *list_count,
+		unsigned int list_capacity, int is_median, cudaStream_t stream);
+
+// ssc_sum.cu
+int launch_sum_accumulate(const ssc_band &b, uint32_t *acc, unsigned long long *maxim, cudaStream_t stream);
+int launch_sum_finish(const uint32_t *acc, size_t count, const unsigned long long *maxim, WORD *out,
+		cudaStream_t stream);
+
+// ssc_stats.cu
+int launch_histogram(const ssc_band &b, uint32_t *hist, cudaStream_t stream);
+int launch_ikss(const uint32_t *hist, int n_frames, double *stats, uint32_t *scratch, cudaStream_t stream);
+int launch_norm_coeffs(const double *stats, int n_frames, int ref_image, int mode, double *coeff,
+		int *status, cudaStream_t stream);
+
+// ssc_synth.cu
+int launch_synth(WORD *frames, int n_frames, int layers, int height, int width, int first_frame,
+		int kind, uint64_t seed, cudaStream_t stream);
+
+}  // namespace ssc

@@ -1,0 +1,415 @@
+// ssc_stats.cu -- K4 / K5 / K6: the normalization statistics.
+//
+// The reference computes, per frame, IKSS location and scale of the non-zero
+// samples of layer 0 by sorting W*H doubles (src/algos/statistics.c:152-187,
+// 277-290, reached through sequence.c:1107-1118 from stacking.c:79-123).
+// Here the same estimator runs on an exact 65536-bin histogram: every clipping
+// window of the sorted-sample form is a run of whole bins, so its medians and
+// MADs are the same order statistics, and histograms of row bands (or GPUs)
+// simply add -- the statistics stay exact under any sharding.
+#include "ssc_device.cuh"
+#include "ssc_kernels.h"
+
+namespace ssc {
+
+// ---------------------------------------------------------------------------
+// K4: histogram of layer 0 of every frame of a band.
+//
+// A CTA owns a shared-memory histogram of all 65536 bins as 16-bit counters
+// packed two per word (128 KB).  It consumes its frame's rows in chunks of at
+// most 65535 samples -- a 16-bit counter cannot overflow within a chunk
+// whatever the data -- then flushes the non-zero words to the global 32-bit
+// histogram.  Global atomics therefore scale with the number of DISTINCT
+// values per chunk, not with the number of samples.
+// ---------------------------------------------------------------------------
+constexpr int HIST_THREADS = 1024;
+constexpr int HIST_CHUNK = 65528;	// multiple of 8, < 65536
+
+__global__ void __launch_bounds__(HIST_THREADS, 1)
+k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
+	extern __shared__ uint32_t sh[];	// 32768 words
+	__shared__ unsigned int any_gt255;
+	const int frame = blockIdx.x / ctas_per_frame;
+	const int part = blockIdx.x % ctas_per_frame;
+	const size_t band_px = (size_t) b.out_rows * b.width;	// layer-0 samples of this band
+	const WORD *src = b.frames + (size_t) frame * b.frame_stride + (size_t) (b.out_row0 - b.buf_row0) * b.width;
+	uint32_t *gh = hist + (size_t) frame * SSC_HIST_STRIDE;
+	const bool vec_ok = ((uintptr_t) src % 16 == 0);
+
+	for (int i = threadIdx.x; i < 32768; i += HIST_THREADS) sh[i] = 0;
+	if (threadIdx.x == 0) any_gt255 = 0;
+	__syncthreads();
+
+	unsigned int seen = 0;
+	const size_t n_chunks = (band_px + HIST_CHUNK - 1) / HIST_CHUNK;
+	for (size_t ch = part; ch < n_chunks; ch += ctas_per_frame) {
+		const size_t beg = ch * HIST_CHUNK;
+		const size_t end = beg + HIST_CHUNK < band_px ? beg + HIST_CHUNK : band_px;
+		if (vec_ok) {
+			const size_t nvec = (end - beg) >> 3;
+			const uint4 *v4 = reinterpret_cast<const uint4 *>(src + beg);
+			for (size_t i = threadIdx.x; i < nvec; i += HIST_THREADS) {
+				uint4 v = __ldg(v4 + i);
+				unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					unsigned int a = w[k] & 0xFFFFu, c = w[k] >> 16;
+					atomicAdd(&sh[a >> 1], 1u << ((a & 1) * 16));
+					atomicAdd(&sh[c >> 1], 1u << ((c & 1) * 16));
+					seen |= a | c;
+				}
+			}
+			for (size_t i = beg + (nvec << 3) + threadIdx.x; i < end; i += HIST_THREADS) {
+				unsigned int a = src[i];
+				atomicAdd(&sh[a >> 1], 1u << ((a & 1) * 16));
+				seen |= a;
+			}
+		} else {
+			for (size_t i = beg + threadIdx.x; i < end; i += HIST_THREADS) {
+				unsigned int a = src[i];
+				atomicAdd(&sh[a >> 1], 1u << ((a & 1) * 16));
+				seen |= a;
+			}
+		}
+		__syncthreads();
+		for (int i = threadIdx.x; i < 32768; i += HIST_THREADS) {
+			uint32_t w = sh[i];
+			if (w) {
+				sh[i] = 0;
+				if (w & 0xFFFFu) atomicAdd(&gh[2 * i], w & 0xFFFFu);
+				if (w >> 16) atomicAdd(&gh[2 * i + 1], w >> 16);
+			}
+		}
+		__syncthreads();
+	}
+	// word 65537: "layer 0 of this band has a sample > 255" (consumed by k_other_layers_gt255)
+	if (seen > 255u) atomicOr(&any_gt255, 1u);
+	__syncthreads();
+	if (threadIdx.x == 0 && any_gt255) atomicOr(&gh[65537], 1u);
+}
+
+// get_normalized_value (src/core/utils.c:454-459) looks at the max over ALL
+// layers.  Only when layer 0 of this band stays <= 255 can the other layers
+// matter; then count their samples > 255 into word 65536.
+__global__ void k_other_layers_gt255(ssc_band b, uint32_t *__restrict__ hist) {
+	const int frame = blockIdx.y;
+	uint32_t *gh = hist + (size_t) frame * SSC_HIST_STRIDE;
+	if (gh[65537] != 0) return;
+	const size_t band_px = (size_t) b.out_rows * b.width;
+	unsigned int cnt = 0;
+	for (int layer = 1; layer < b.layers; layer++) {
+		const WORD *src = b.frames + (size_t) frame * b.frame_stride + (size_t) layer * b.layer_stride
+				+ (size_t) (b.out_row0 - b.buf_row0) * b.width;
+		for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < band_px;
+				i += (size_t) gridDim.x * blockDim.x)
+			cnt += src[i] > 255;
+	}
+	for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&gh[65536], cnt);
+}
+
+int launch_histogram(const ssc_band &b, uint32_t *hist, cudaStream_t stream) {
+	if (b.n_frames < 1) return SSC_ERR_ARG;
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4) != cudaSuccess)
+		return SSC_ERR_CUDA;
+	const size_t band_px = (size_t) b.out_rows * b.width;
+	const size_t n_chunks = (band_px + HIST_CHUNK - 1) / HIST_CHUNK;
+	// one CTA per SM is resident (128 KB of shared memory): spread every frame over
+	// enough CTAs to fill the machine about twice
+	int per_frame = (2 * sms + b.n_frames - 1) / b.n_frames;
+	if ((size_t) per_frame > n_chunks) per_frame = (int) n_chunks;
+	if (per_frame < 1) per_frame = 1;
+	k_histogram<<<b.n_frames * per_frame, HIST_THREADS, 32768 * 4, stream>>>(b, hist, per_frame);
+	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
+	if (b.layers > 1) {
+		dim3 grid(8, b.n_frames);
+		k_other_layers_gt255<<<grid, 256, 0, stream>>>(b, hist);
+		if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
+	}
+	return SSC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K5: IKSS per frame from the histogram.  One CTA of 1024 threads per frame.
+// Restates statistics.c:152-187 exactly as oracle/siril_oracle.c so_ikss_hist
+// does (same summation order for the biweight sums -> bit-identical doubles).
+// ---------------------------------------------------------------------------
+constexpr int IKSS_THREADS = 1024;
+
+// terms of siril_stats_double_bwmv, statistics.c:136-145
+__device__ __forceinline__ void bwmv_term(double d, double m, double mad9, double &up, double &down) {
+	double dm = dsub(d, m);
+	double yi = ddiv(dm, mad9);
+	double yi2 = dmul(yi, yi);
+	double ai = (fabs(yi) < 1.0) ? 1.0 : 0.0;
+	double omy = dsub(1.0, yi2);
+	double omy2 = dmul(omy, omy);
+	up = dmul(dmul(ai, dmul(dm, dm)), dmul(omy2, omy2));
+	down = dmul(dmul(ai, omy), dsub(1.0, dmul(5.0, yi2)));
+}
+
+__global__ void __launch_bounds__(IKSS_THREADS, 1)
+k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *__restrict__ scratch, int n_frames) {
+	const int frame = blockIdx.x;
+	const int tid = threadIdx.x;
+	const uint32_t *h = hist + (size_t) frame * SSC_HIST_STRIDE;
+	uint32_t *cum = scratch + (size_t) frame * 65536;	// inclusive prefix counts, cum[0] = 0 (zeros excluded)
+
+	__shared__ double pu[IKSS_THREADS], pd[IKSS_THREADS];
+	__shared__ uint32_t wsum[32];
+	__shared__ int s_bi, s_bj, s_done, s_top;
+	__shared__ double s_m, s_mad, s_norm, s_loc, s_scale, s_s0;
+	__shared__ unsigned long long s_n;
+
+	// --- prefix sums: thread t owns bins [64t, 64t+64) ---
+	uint32_t local = 0;
+	int top = 0;
+	for (int k = 0; k < 64; k++) {
+		int bin = tid * 64 + k;
+		uint32_t c = bin == 0 ? 0u : h[bin];
+		local += c;
+		if (c) top = bin;
+	}
+	uint32_t incl = local;
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+		if ((tid & 31) >= o) incl += v;
+	}
+	int wtop = top;
+	for (int o = 16; o > 0; o >>= 1) wtop = max(wtop, __shfl_xor_sync(0xffffffffu, wtop, o));
+	if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+	if (tid == 0) s_top = 0;
+	__syncthreads();
+	if ((tid & 31) == 0) atomicMax(&s_top, wtop);
+	if (tid < 32) {
+		uint32_t v = wsum[tid], inc = v;
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+			if (tid >= o) inc += u;
+		}
+		wsum[tid] = inc - v;	// exclusive warp offsets
+	}
+	__syncthreads();
+	uint32_t run = wsum[tid >> 5] + incl - local;
+	for (int k = 0; k < 64; k++) {
+		int bin = tid * 64 + k;
+		run += bin == 0 ? 0u : h[bin];
+		cum[bin] = run;
+	}
+	__syncthreads();
+
+	if (tid == 0) {
+		// hist_size - 1: 255 when the frame's max over all layers is <= 255 (gui/histogram.c:116)
+		s_norm = (s_top <= 255 && h[65536] == 0) ? 255.0 : 65535.0;
+		s_bi = 1;
+		s_bj = 65536;
+		s_done = 0;
+		s_s0 = 1.0;
+		s_loc = s_scale = 0.0;
+	}
+	__syncthreads();
+	const double norm = s_norm;
+	const unsigned long long n_total = cum[65535];
+
+	for (int it = 0; it < SSC_ITER_CAP; it++) {
+		if (tid == 0) {
+			const int bi = s_bi, bj = s_bj;
+			const unsigned long long base = cum[bi - 1];
+			const unsigned long long n = bj > bi ? (unsigned long long) cum[bj - 1] - base : 0ull;
+			s_n = n;
+			if (n < 1) {		// statistics.c:161-164
+				s_loc = s_scale = 0.0;
+				s_done = 1;
+			} else {
+				// median: bins holding ranks (n-1)/2 and n/2 (gsl_stats_median_from_sorted_data)
+				unsigned long long rk[2] = {(n - 1) >> 1, n >> 1};
+				int kb[2];
+				for (int q = 0; q < 2; q++) {
+					int lo = bi, hi = bj - 1;	// smallest k with cum[k] - base > rank
+					while (lo < hi) {
+						int mid = (lo + hi) >> 1;
+						if ((unsigned long long) cum[mid] - base > rk[q]) hi = mid; else lo = mid + 1;
+					}
+					kb[q] = lo;
+				}
+				double dl = ddiv((double) kb[0], norm), dr = ddiv((double) kb[1], norm);
+				double m = rk[0] == rk[1] ? dl : ddiv(dadd(dl, dr), 2.0);
+				// MAD (statistics.c:83-100): order statistics of |d_k - m|.  With M2 = kb0 + kb1
+				// (twice the median in bin units) bins order by the integer distance
+				// u_k = |2k - M2|; only the mirror pair (k, M2 - k) ties, and there the FP
+				// deltas decide.  C(u) = samples with u_k <= u, from the prefix counts.
+				const int M2 = kb[0] + kb[1];
+				double dv[2];
+				for (int q = 0; q < 2; q++) {
+					int ulo = 0, uhi = 2 * 65536;
+					while (ulo < uhi) {
+						int u = (ulo + uhi) >> 1;
+						int khi = (M2 + u) >> 1;			// floor((M2+u)/2)
+						int klo = M2 - u >= 0 ? (M2 - u + 1) >> 1 : 0;	// ceil((M2-u)/2)
+						if (khi > bj - 1) khi = bj - 1;
+						if (klo < bi) klo = bi;
+						unsigned long long cnt = khi >= klo ? (unsigned long long) cum[khi] - cum[klo - 1] : 0ull;
+						if (cnt > rk[q]) uhi = u; else ulo = u + 1;
+					}
+					const int u = ulo;
+					unsigned long long below = 0;	// C(u - 1)
+					if (u > 0) {
+						int khi = (M2 + u - 1) >> 1;
+						int klo = M2 - (u - 1) >= 0 ? (M2 - (u - 1) + 1) >> 1 : 0;
+						if (khi > bj - 1) khi = bj - 1;
+						if (klo < bi) klo = bi;
+						below = khi >= klo ? (unsigned long long) cum[khi] - cum[klo - 1] : 0ull;
+					}
+					const int k1 = (M2 - u) >> 1, k2 = (M2 + u) >> 1;	// exact: u has M2's parity here
+					const bool in1 = (M2 - u) >= 0 && k1 >= bi && k1 < bj;
+					const bool in2 = k2 != k1 && k2 >= bi && k2 < bj;
+					const unsigned long long c1 = in1 ? (unsigned long long) cum[k1] - cum[k1 - 1] : 0ull;
+					const double d1 = fabs(dsub(ddiv((double) k1, norm), m));
+					const double d2 = fabs(dsub(ddiv((double) k2, norm), m));
+					const unsigned long long pos = rk[q] - below;
+					if (!in2) dv[q] = d1;
+					else if (!in1) dv[q] = d2;
+					else if (d1 <= d2) dv[q] = pos < c1 ? d1 : d2;
+					else {
+						const unsigned long long c2 = (unsigned long long) cum[k2] - cum[k2 - 1];
+						dv[q] = pos < c2 ? d2 : d1;
+					}
+				}
+				s_m = m;
+				s_mad = rk[0] == rk[1] ? dv[0] : ddiv(dadd(dv[0], dv[1]), 2.0);
+			}
+		}
+		__syncthreads();
+		if (s_done) break;
+
+		// --- biweight midvariance sums (statistics.c:128-150), count * term per bin ---
+		const double m = s_m, mad = s_mad;
+		const int bi = s_bi, bj = s_bj;
+		double u = 0.0, w = 0.0;
+		if (mad > 0.0) {
+			const double mad9 = dmul(9.0, mad);
+			for (int k = 0; k < 64; k++) {
+				int bin = tid * 64 + k;
+				if (bin < bi || bin >= bj) continue;
+				uint32_t c = h[bin];
+				if (c == 0) continue;
+				double tu, tw;
+				bwmv_term(ddiv((double) bin, norm), m, mad9, tu, tw);
+				u = dadd(u, dmul((double) c, tu));
+				w = dadd(w, dmul((double) c, tw));
+			}
+		}
+		pu[tid] = u;
+		pd[tid] = w;
+		__syncthreads();
+		for (int stride = IKSS_THREADS / 2; stride >= 1; stride >>= 1) {
+			if (tid < stride) {
+				pu[tid] = dadd(pu[tid], pu[tid + stride]);
+				pd[tid] = dadd(pd[tid], pd[tid + stride]);
+			}
+			__syncthreads();
+		}
+
+		if (tid == 0) {
+			double bw = 0.0;
+			if (mad > 0.0) {
+				double down = pd[0];
+				bw = dmul((double) (long long) s_n, ddiv(pu[0], dmul(down, down)));
+			}
+			const double s = dsqrt(bw);
+			if (s < 2E-23) {			// statistics.c:168-172
+				s_loc = m;
+				s_scale = 0.0;
+				s_done = 1;
+			} else if (ddiv(dsub(s_s0, s), s) < 10E-6) {	// :173-177
+				s_loc = m;
+				s_scale = dmul(0.991, s);
+				s_done = 1;
+			} else {				// :178-184
+				s_s0 = s;
+				const double xlow = dsub(m, dmul(4.0, s)), xhigh = dadd(m, dmul(4.0, s));
+				int nbi = bi, nbj = bj;
+				{	// first bin >= bi with d_k >= xlow
+					double g = dmul(xlow, norm);
+					int k = g > 3.0 ? (int) g - 2 : 0;
+					if (k < bi) k = bi;
+					while (k < bj && ddiv((double) k, norm) < xlow) k++;
+					nbi = k;
+				}
+				{	// last bin < bj with d_k <= xhigh
+					double g = dmul(xhigh, norm);
+					int k = g < 65533.0 ? (int) g + 2 : 65535;
+					if (k > bj - 1) k = bj - 1;
+					while (k >= nbi && ddiv((double) k, norm) > xhigh) k--;
+					nbj = k + 1;
+				}
+				s_bi = nbi;
+				s_bj = nbj;
+			}
+		}
+		__syncthreads();
+		if (s_done) break;
+	}
+
+	if (tid == 0) {
+		stats[0 * n_frames + frame] = dmul(s_loc, norm);	// statistics.c:287-288
+		stats[1 * n_frames + frame] = dmul(s_scale, norm);
+		stats[2 * n_frames + frame] = norm;
+		stats[3 * n_frames + frame] = (double) (long long) n_total;
+	}
+}
+
+int launch_ikss(const uint32_t *hist, int n_frames, double *stats, uint32_t *scratch, cudaStream_t stream) {
+	if (n_frames < 1) return SSC_ERR_ARG;
+	k_ikss<<<n_frames, IKSS_THREADS, 0, stream>>>(hist, stats, scratch, n_frames);
+	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------
+// K6: _compute_normalization_for_image for all frames (stacking.c:95-121,
+// defaults :130-134, reference index :143-145).
+// ---------------------------------------------------------------------------
+__global__ void k_norm_coeffs(const double *__restrict__ stats, int n, int ref, int mode,
+		double *__restrict__ coeff, int *status) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double *location = stats, *scale_in = stats + n, *ngood = stats + 3 * n;
+	double offset = 0.0, mul = 1.0, scale = 1.0;
+	if (ref < 0 || ref >= n) ref = 0;
+	if (mode != NO_NORM) {
+		if (ngood[i] < 1.0 && status) atomicExch(status, 1);	// statistics() would return NULL (:247-250)
+		const double scale0 = scale_in[ref], loc0 = location[ref];
+		switch (mode) {
+		default:
+		case ADDITIVE_SCALING:
+			scale = ddiv(scale0, scale_in[i]);
+			offset = dsub(dmul(scale, location[i]), loc0);
+			break;
+		case ADDITIVE:
+			offset = dsub(dmul(scale, location[i]), loc0);
+			break;
+		case MULTIPLICATIVE_SCALING:
+			scale = ddiv(scale0, scale_in[i]);
+			mul = ddiv(loc0, location[i]);
+			break;
+		case MULTIPLICATIVE:
+			mul = ddiv(loc0, location[i]);
+			break;
+		}
+	}
+	coeff[i] = offset;
+	coeff[n + i] = mul;
+	coeff[2 * n + i] = scale;
+}
+
+int launch_norm_coeffs(const double *stats, int n_frames, int ref_image, int mode, double *coeff,
+		int *status, cudaStream_t stream) {
+	if (n_frames < 1) return SSC_ERR_ARG;
+	k_norm_coeffs<<<(n_frames + 127) / 128, 128, 0, stream>>>(stats, n_frames, ref_image, mode, coeff, status);
+	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
+}
+
+}  // namespace ssc

@@ -1,0 +1,240 @@
+"""Parity of the CUDA library with the oracle -- the parity tests proper (`-m gpu`).
+
+Everything goes through the C ABI (ssc_stack_* / ssc_dev_* in libsiril_stack_cuda.so).
+Bars (BASELINE.json north_star): sum and median bit-exact; the floating-point rejection modes
+bit-exact against the oracle evaluated with the same sigma formulation, and against the
+reference formulation (GSL's x87 long double) at most +-1 ADU on <= 0.01 % of the pixels with
+identical rejection counters.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+REJ = {"none": (0, (0, 0)), "percentile": (1, (0.2, 0.1)), "sigma": (2, (4.0, 3.0)),
+       "sigmedian": (3, (4.0, 3.0)), "winsorized": (4, (4.0, 3.0)), "linearfit": (5, (5.0, 2.5))}
+
+
+def close_enough(a, b, frac=1e-4):
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    return d.max() <= 1 and (d != 0).sum() <= max(1, int(frac * d.size))
+
+
+# --------------------------------------------------------------------------- median
+@pytest.mark.parametrize("n,c,h,w", [(2, 1, 8, 8), (3, 1, 9, 17), (5, 3, 12, 24), (32, 1, 40, 64),
+                                     (33, 1, 16, 40), (64, 1, 16, 48), (100, 1, 8, 24), (257, 1, 4, 16)])
+def test_median_bit_exact(gpu, port, n, c, h, w):
+    fr = synth.make_random(n, c, h, w, seed=n * 7 + c)
+    res = gpu.stack_median(gpu.Sequence(fr))
+    assert np.array_equal(res.data, port.stack_median(fr)["out"])
+
+
+def test_median_ties_and_extremes(gpu, port):
+    fr = synth.make_random(16, 1, 16, 32, seed=1, lo=0, hi=3)          # heavy ties
+    fr[:, 0, 0, :8] = 65535
+    fr[:8, 0, 1, :8] = 0
+    fr[8:, 0, 1, :8] = 65535                                            # (0 + 65535) / 2 truncated
+    res = gpu.stack_median(gpu.Sequence(fr))
+    assert np.array_equal(res.data, port.stack_median(fr)["out"])
+    assert res.data[0, 1, 0] == 32767 and res.data[0, 0, 0] == 65535
+
+
+@pytest.mark.parametrize("norm", [1, 2, 3, 4])
+def test_median_normalized(gpu, port, norm):
+    fr = synth.make_frames(12, 1, 48, 64, seed=5)
+    res = gpu.stack_median(gpu.Sequence(fr), normalize=norm, want_coeff=True)
+    assert np.array_equal(res.data, port.stack_median(fr, normalize=norm, coeff=res.coeff)["out"])
+
+
+def test_median_ser_order_and_subset(gpu, port):
+    fr = synth.make_random(9, 3, 10, 16, seed=2)
+    res = gpu.stack_median(gpu.Sequence(fr, row_order=gpu.ROWS_SER))
+    assert np.array_equal(res.data, port.stack_median(fr, row_order=1)["out"])
+    idx = [7, 1, 4, 2, 8]                                               # image_indices: a filtered, reordered list
+    res = gpu.stack_median(gpu.Sequence(fr), image_indices=idx)
+    assert np.array_equal(res.data, port.stack_median(fr[idx])["out"])
+
+
+# --------------------------------------------------------------------------- sum
+@pytest.mark.parametrize("hi", [300, 65536])
+@pytest.mark.parametrize("c,w", [(1, 32), (3, 24), (1, 21)])
+def test_sum_bit_exact(gpu, port, hi, c, w):
+    fr = synth.make_random(16, c, 16, w, seed=11, hi=hi)
+    res = gpu.stack_summing(gpu.Sequence(fr))
+    p = port.stack_sum(fr)
+    assert np.array_equal(res.data, p["out"])
+    assert (res.data.reshape(c, -1)[:, 0] == 0).all()
+    assert res.hi == min(p["maxim"], 65535)
+
+
+def test_sum_shifts_and_ser(gpu, port):
+    fr = synth.make_random(6, 1, 20, 32, seed=4, hi=4000)
+    sx = [0, 2, -3, 1, 0, -1]
+    sy = [0, -2, 1, 3, -1, 0]
+    for ro in (0, 1):
+        res = gpu.stack_summing(gpu.Sequence(fr, shiftx=sx, shifty=sy, row_order=ro))
+        assert np.array_equal(res.data, port.stack_sum(fr, shiftx=sx, shifty=sy, row_order=ro)["out"]), ro
+        res = gpu.stack_summing(gpu.Sequence(fr, row_order=ro))
+        assert np.array_equal(res.data, port.stack_sum(fr, row_order=ro)["out"]), ro
+
+
+def test_sum_filter_callback(gpu, port):
+    fr = synth.make_random(8, 1, 8, 16, seed=6, hi=500)
+    keep = [0, 2, 3, 6]
+    crit = gpu.FILTER_FN(lambda seq, i, p: int(i in keep))
+    res = gpu.stack_summing(gpu.Sequence(fr), filtering_criterion=crit)
+    assert np.array_equal(res.data, port.stack_sum(fr[keep])["out"])
+
+
+# --------------------------------------------------------------------------- mean with rejection
+@pytest.mark.parametrize("rej", list(REJ))
+@pytest.mark.parametrize("norm", [0, 1, 2, 3, 4])
+def test_mean_all_modes(gpu, port, rej, norm):
+    rj, sig = REJ[rej]
+    fr = synth.make_frames(40, 1, 32, 48, seed=3, outlier_p=4e-3, zero_p=1e-3, stars=4)
+    res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), rj, sig, norm)
+    coeff = res.coeff
+    same = port.stack_mean(fr, rj, sig, norm, coeff=coeff, sd_mode=port.SD_EXACT)
+    assert np.array_equal(res.data, same["out"])                        # same formulation: bit-exact
+    assert np.array_equal(res.irej, same["irej"])
+    assert res.guard_fired == same["guard_fired"] and res.cap_hit == 0
+    gsl = port.stack_mean(fr, rj, sig, norm, coeff=coeff, sd_mode=port.SD_GSL)
+    assert close_enough(res.data, gsl["out"])                           # reference formulation
+    if same["guard_fired"] == 0:
+        assert np.array_equal(res.irej, gsl["irej"])
+
+
+@pytest.mark.parametrize("rej", ["sigma", "winsorized", "linearfit", "percentile"])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 8, 17, 64, 130])
+def test_mean_frame_counts(gpu, port, rej, n):
+    rj, sig = REJ[rej]
+    fr = synth.make_frames(n, 1, 16, 32, seed=n, outlier_p=1e-2, zero_p=2e-3, stars=2)
+    res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), rj, sig)
+    same = port.stack_mean(fr, rj, sig, sd_mode=port.SD_EXACT)
+    assert np.array_equal(res.data, same["out"])
+    assert np.array_equal(res.irej, same["irej"])
+    assert res.guard_fired == same["guard_fired"]                      # small N: the guard does fire
+
+
+def test_mean_rgb_ser_and_reference_image(gpu, port):
+    fr = synth.make_frames(16, 3, 16, 24, seed=9, outlier_p=4e-3)
+    for ro in (0, 1):
+        res = gpu.stack_mean_with_rejection(gpu.Sequence(fr, row_order=ro, reference_image=3), 2, (4, 3), 2)
+        same = port.stack_mean(fr, 2, (4, 3), 2, coeff=res.coeff, row_order=ro, sd_mode=port.SD_EXACT)
+        assert np.array_equal(res.data, same["out"])
+        assert np.array_equal(res.irej, same["irej"])
+        assert res.coeff[1, 3] == 1.0                                   # the reference frame is the identity
+
+
+def test_mean_with_shifts(gpu, port):
+    fr = synth.make_frames(12, 1, 64, 40, seed=21)
+    sx = [0, 3, -2, 1, 0, -4, 2, 0, 1, -1, 0, 2]
+    sy = [0, -3, 2, 4, -1, 0, 1, -2, 3, 0, -4, 1]
+    for ro in (0, 1):
+        for norm in (0, 3):
+            res = gpu.stack_mean_with_rejection(gpu.Sequence(fr, shiftx=sx, shifty=sy, row_order=ro), 2, (4, 3), norm)
+            same = port.stack_mean(fr, 2, (4, 3), norm, coeff=res.coeff, shiftx=sx, shifty=sy, row_order=ro,
+                                   sd_mode=port.SD_EXACT)
+            assert np.array_equal(res.data, same["out"]), (ro, norm)
+            assert np.array_equal(res.irej, same["irej"])
+
+
+def test_mean_extremes(gpu, port):
+    """Saturated, all-zero and two-valued columns; negative sigma parameters (everything is flagged)."""
+    fr = synth.make_random(20, 1, 8, 32, seed=5)
+    fr[:, 0, 0] = 65535
+    fr[:, 0, 1] = 0
+    fr[:10, 0, 2] = 0
+    fr[10:, 0, 2] = 65535
+    fr[:, 0, 3] = 1
+    for rej in REJ:
+        rj, sig = REJ[rej]
+        for s in (sig, (-1.0, -1.0)):
+            res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), rj, s)
+            same = port.stack_mean(fr, rj, s, sd_mode=port.SD_EXACT)
+            assert np.array_equal(res.data, same["out"]), (rej, s)
+            assert np.array_equal(res.irej, same["irej"]), (rej, s)
+            assert res.guard_fired == same["guard_fired"]
+
+
+# --------------------------------------------------------------------------- normalization statistics
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+def test_coefficients(gpu, port, mode):
+    fr = synth.make_frames(9, 3, 96, 128, seed=13, zero_p=3e-3)
+    c = gpu.compute_normalization(gpu.Sequence(fr, reference_image=2), mode)
+    hist_stats = [port.frame_stats_hist(f) for f in fr]
+    expect = port.norm_coeffs(mode, [s[0] for s in hist_stats], [s[1] for s in hist_stats], ref_image=2)
+    assert np.array_equal(c, expect)                                    # same algorithm, same summation order
+    sorted_stats = [port.frame_stats_sorted(f) for f in fr]
+    ref = port.norm_coeffs(mode, [s[0] for s in sorted_stats], [s[1] for s in sorted_stats], ref_image=2)
+    assert np.allclose(c, ref, rtol=1e-11, atol=1e-9)                   # the reference's sort-based form
+    if mode in (1, 2):
+        assert np.array_equal(c, ref)                                   # location only: exact
+
+
+def test_coefficients_8bit_range_and_zeros(gpu, port):
+    fr = synth.make_random(4, 3, 32, 32, seed=1, lo=0, hi=200)          # max <= 255: hist_size 256
+    c = gpu.compute_normalization(gpu.Sequence(fr), 3)
+    st = [port.frame_stats_sorted(f) for f in fr]
+    assert all(s[2] == 255.0 for s in st)
+    assert np.allclose(c, port.norm_coeffs(3, [s[0] for s in st], [s[1] for s in st]), rtol=1e-11)
+    fr[1, 2, 3, 3] = 300                                                # another layer lifts one frame's max
+    c = gpu.compute_normalization(gpu.Sequence(fr), 3)
+    st = [port.frame_stats_sorted(f) for f in fr]
+    assert st[1][2] == 65535.0 and st[0][2] == 255.0
+    assert np.allclose(c, port.norm_coeffs(3, [s[0] for s in st], [s[1] for s in st]), rtol=1e-11)
+
+
+def test_all_zero_frame_is_an_error(gpu):
+    fr = synth.make_frames(4, 1, 16, 16, seed=2)
+    fr[2] = 0
+    with pytest.raises(gpu.StackError) as e:
+        gpu.stack_mean_with_rejection(gpu.Sequence(fr), 2, (4, 3), 1)
+    assert e.value.code == -1                                           # the reference: "no data computed", -1
+
+
+# --------------------------------------------------------------------------- golden fixtures (made from oracle/_ref)
+def test_golden_fixtures(gpu):
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+    assert files
+    for f in files:
+        g = np.load(f)
+        fr, kind = g["frames"], str(g["kind"])
+        seq = gpu.Sequence(fr)
+        if kind == "median":
+            res = gpu.stack_median(seq, normalize=int(g["normalize"]))
+            assert np.array_equal(res.data, g["out"]), f
+        elif kind == "sum":
+            assert np.array_equal(gpu.stack_summing(seq).data, g["out"]), f
+        else:
+            rj = int(g["rejection"])
+            res = gpu.stack_mean_with_rejection(seq, rj, tuple(g["sig"]), int(g["normalize"]))
+            assert close_enough(res.data, g["out"], frac=2e-3), f       # tiny images: allow one pixel
+            if rj in (0, 1, 5):
+                assert np.array_equal(res.data, g["out"]), f            # no long double involved: exact
+            assert np.array_equal(res.irej, g["irej"]), f
+            if int(g["normalize"]):
+                assert np.allclose(res.coeff, g["coeff"], rtol=1e-11, atol=1e-9), f
+
+
+# --------------------------------------------------------------------------- callbacks, cancel
+def test_callbacks_and_cancel(gpu):
+    fr = synth.make_frames(8, 1, 16, 16, seed=3)
+    logs = []
+    gpu.set_callbacks(log=logs.append)
+    try:
+        gpu.stack_mean_with_rejection(gpu.Sequence(fr), 2, (4, 3), 1)
+        assert any("Pixel rejection in channel #0" in m for m in logs)
+        assert any("Computing normalization" in m for m in logs)
+        gpu.set_callbacks(should_continue=lambda: False)
+        with pytest.raises(gpu.StackError) as e:
+            gpu.stack_median(gpu.Sequence(fr))
+        assert e.value.code == -1                                       # cancelled: -1, as the reference
+    finally:
+        gpu.set_callbacks()
