@@ -252,9 +252,12 @@ int ssc_dev_norm_coeffs(const double *stats, int n_frames, int ref_image, int mo
 		double *coeff, int *status, void *stream);
 
 /* Counter-based synthetic frames for benchmarks and large-size
- * property tests: fills device WORD [n_frames][layers][height][width]. */
-int ssc_dev_synth_frames(WORD *frames, int n_frames, int layers, int height, int width,
-		int first_frame, int kind, uint64_t seed, void *stream);
+ * property tests: fills device WORD [n_frames][layers][rows][width] with storage
+ * rows [row0, row0+rows) of frames first_frame.. of a full_height-row image; every
+ * sample depends only on (seed, kind, frame, layer, y, x), so any band on any GPU
+ * regenerates the same pixels.  kind 0 = deep-sky field, 1 = planetary disc. */
+int ssc_dev_synth_frames(WORD *frames, int n_frames, int layers, int rows, int width,
+		int first_frame, int row0, int full_height, int kind, uint64_t seed, void *stream);
 
 #ifdef __cplusplus
 }

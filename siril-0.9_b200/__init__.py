@@ -150,7 +150,7 @@ _lib.ssc_dev_histogram.argtypes = [C.POINTER(Band), C.c_void_p, C.c_void_p]
 _lib.ssc_dev_ikss.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.ssc_dev_norm_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.ssc_dev_synth_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                      C.c_uint64, C.c_void_p]
+                                      C.c_int, C.c_int, C.c_uint64, C.c_void_p]
 _libc = C.CDLL(None)
 _libc.free.argtypes = [C.c_void_p]
 
@@ -391,7 +391,8 @@ class dev:
                    "ssc_dev_norm_coeffs")
 
     @staticmethod
-    def synth_frames(frames_ptr, n_frames, layers, height, width, first_frame=0, kind=0,
-                     seed=0x5349524C, stream=0):
-        dev._check(_lib.ssc_dev_synth_frames(frames_ptr, n_frames, layers, height, width, first_frame, kind,
-                                             seed, stream), "ssc_dev_synth_frames")
+    def synth_frames(frames_ptr, n_frames, layers, rows, width, first_frame=0, row0=0, full_height=None,
+                     kind=0, seed=0x5349524C, stream=0):
+        full_height = rows if full_height is None else full_height
+        dev._check(_lib.ssc_dev_synth_frames(frames_ptr, n_frames, layers, rows, width, first_frame, row0,
+                                             full_height, kind, seed, stream), "ssc_dev_synth_frames")

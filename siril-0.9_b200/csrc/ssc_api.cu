@@ -167,10 +167,10 @@ int ssc_dev_norm_coeffs(const double *stats, int n_frames, int ref_image, int mo
 	return SSC_OK;
 }
 
-int ssc_dev_synth_frames(WORD *frames, int n_frames, int layers, int height, int width, int first_frame,
-		int kind, uint64_t seed, void *stream) {
-	int rc = ssc::launch_synth(frames, n_frames, layers, height, width, first_frame, kind, seed,
-			(cudaStream_t) stream);
+int ssc_dev_synth_frames(WORD *frames, int n_frames, int layers, int rows, int width, int first_frame,
+		int row0, int full_height, int kind, uint64_t seed, void *stream) {
+	int rc = ssc::launch_synth(frames, n_frames, layers, rows, width, first_frame, row0, full_height, kind,
+			seed, (cudaStream_t) stream);
 	if (rc) return fail(rc, "synth launch failed");
 	return SSC_OK;
 }

@@ -36,7 +36,7 @@ int launch_norm_coeffs(const double *stats, int n_frames, int ref_image, int mod
 		int *status, cudaStream_t stream);
 
 // ssc_synth.cu
-int launch_synth(WORD *frames, int n_frames, int layers, int height, int width, int first_frame,
-		int kind, uint64_t seed, cudaStream_t stream);
+int launch_synth(WORD *frames, int n_frames, int layers, int rows, int width, int first_frame,
+		int row0, int full_height, int kind, uint64_t seed, cudaStream_t stream);
 
 }  // namespace ssc

@@ -18,13 +18,13 @@ __device__ __forceinline__ float u01(uint32_t v) { return ((float) v + 0.5f) * (
 
 // kind 0: deep-sky field (background + sky gradient + star grid + noise + outliers + dead samples)
 // kind 1: planetary disc (limb-darkened disc, strong noise, no stars)
-__global__ void k_synth(WORD *__restrict__ frames, int n_frames, int layers, int height, int width,
-		int first_frame, int kind, uint64_t seed) {
-	const size_t plane = (size_t) height * width;
+__global__ void k_synth(WORD *__restrict__ frames, int n_frames, int layers, int rows, int width,
+		int first_frame, int row0, int height, int kind, uint64_t seed) {
+	const size_t plane = (size_t) rows * width;
 	const size_t total = plane * layers;
 	for (size_t g = (size_t) blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t) gridDim.x * blockDim.x) {
 		const int x = (int) (g % width);
-		const int y = (int) ((g / width) % height);
+		const int y = row0 + (int) ((g / width) % rows);
 		const int c = (int) (g / plane);
 		const float chan_gain = layers == 1 ? 1.0f : (c == 0 ? 0.8f : (c == 1 ? 1.0f : 0.6f));
 		float fixed_signal = 0.0f, sky = 0.0f;
@@ -75,12 +75,14 @@ __global__ void k_synth(WORD *__restrict__ frames, int n_frames, int layers, int
 	}
 }
 
-int launch_synth(WORD *frames, int n_frames, int layers, int height, int width, int first_frame,
-		int kind, uint64_t seed, cudaStream_t stream) {
-	if (n_frames < 1 || layers < 1 || height < 1 || width < 1) return SSC_ERR_ARG;
-	size_t total = (size_t) layers * height * width;
+int launch_synth(WORD *frames, int n_frames, int layers, int rows, int width, int first_frame,
+		int row0, int full_height, int kind, uint64_t seed, cudaStream_t stream) {
+	if (n_frames < 1 || layers < 1 || rows < 1 || width < 1 || row0 < 0 || row0 + rows > full_height)
+		return SSC_ERR_ARG;
+	size_t total = (size_t) layers * rows * width;
 	unsigned int grid = (unsigned int) ((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-	k_synth<<<grid, 256, 0, stream>>>(frames, n_frames, layers, height, width, first_frame, kind, seed);
+	k_synth<<<grid, 256, 0, stream>>>(frames, n_frames, layers, rows, width, first_frame, row0, full_height,
+			kind, seed);
 	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
 }
 

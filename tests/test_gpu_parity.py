@@ -195,8 +195,11 @@ def test_all_zero_frame_is_an_error(gpu):
     fr = synth.make_frames(4, 1, 16, 16, seed=2)
     fr[2] = 0
     with pytest.raises(gpu.StackError) as e:
-        gpu.stack_mean_with_rejection(gpu.Sequence(fr), 2, (4, 3), 1)
-    assert e.value.code == -1                                           # the reference: "no data computed", -1
+        gpu.stack_mean_with_rejection(gpu.Sequence(fr), 2, (4, 3), 1, want_coeff=False)
+    assert e.value.code == -1                                           # the stackers: -1 (stacking.c:1337-1340)
+    with pytest.raises(gpu.StackError) as e:
+        gpu.compute_normalization(gpu.Sequence(fr), 1)
+    assert e.value.code == 1                                            # compute_normalization itself: 1 (:161,189)
 
 
 # --------------------------------------------------------------------------- golden fixtures (made from oracle/_ref)
