@@ -179,6 +179,9 @@ int ssc_compute_normalization(struct stacking_args *args, norm_coeff *coeff, nor
  * bands over these devices (default: device 0 only). */
 int ssc_set_devices(const int *device_ids, int count);
 int ssc_device_count(void);
+/* Diagnostic: 0 = pick the kernel by shape (default), 1 = always use the general
+ * shared-memory kernel.  Both give identical results (tests/test_gpu_parity.py). */
+int ssc_set_kernel_path(int mode);
 const char *ssc_last_error(void);
 const char *ssc_version(void);
 

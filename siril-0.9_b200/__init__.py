@@ -123,7 +123,7 @@ class Callbacks(C.Structure):
 EXPORTS = [
     "ssc_bind_sequence", "ssc_unbind_sequence", "ssc_set_callbacks", "ssc_take_result",
     "ssc_stack_summing", "ssc_stack_median", "ssc_stack_mean_with_rejection",
-    "ssc_compute_normalization", "ssc_set_devices", "ssc_device_count", "ssc_last_error",
+    "ssc_compute_normalization", "ssc_set_devices", "ssc_device_count", "ssc_set_kernel_path", "ssc_last_error",
     "ssc_version", "ssc_dev_stack_median", "ssc_dev_stack_mean", "ssc_dev_sum_accumulate",
     "ssc_dev_sum_finish", "ssc_dev_histogram", "ssc_dev_ikss", "ssc_dev_norm_coeffs",
     "ssc_dev_synth_frames",
@@ -165,6 +165,13 @@ def version():
 
 def device_count():
     return _lib.ssc_device_count()
+
+
+def set_kernel_path(mode):
+    """0 = automatic kernel choice, 1 = general kernel only (diagnostic)."""
+    rc = _lib.ssc_set_kernel_path(int(mode))
+    if rc:
+        raise StackError(rc, "ssc_set_kernel_path")
 
 
 def set_devices(ids):

@@ -84,6 +84,12 @@ extern "C" {
 const char *ssc_last_error(void) { return g_err.c_str(); }
 const char *ssc_version(void) { return "siril-stack-cuda 0.1 (sm_100a)"; }
 
+int ssc_set_kernel_path(int mode) {
+	if (mode < 0 || mode > 1) return fail(SSC_ERR_ARG, "kernel path must be 0 (automatic) or 1 (general kernel only)");
+	ssc::g_kernel_path = mode;
+	return SSC_OK;
+}
+
 int ssc_device_count(void) {
 	int n = 0;
 	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -103,7 +109,7 @@ int ssc_dev_stack_median(const ssc_band *band, int normalize, const double *coef
 	p.out_layer_stride = out_layer_stride;
 	p.out_buf_row0 = out_buf_row0;
 	p.counters = nullptr;
-	rc = ssc::launch_stack_generic(p, nullptr, nullptr, 0, 1, (cudaStream_t) stream);
+	rc = ssc::launch_stack(p, 1, (cudaStream_t) stream);
 	if (rc) return fail(rc, "stack_median launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
 	return SSC_OK;
 }
@@ -126,7 +132,7 @@ int ssc_dev_stack_mean(const ssc_band *band, int normalize, const double *coeff,
 	p.out_layer_stride = out_layer_stride;
 	p.out_buf_row0 = out_buf_row0;
 	p.counters = reinterpret_cast<unsigned long long *>(counters);
-	rc = ssc::launch_stack_generic(p, nullptr, nullptr, 0, 0, (cudaStream_t) stream);
+	rc = ssc::launch_stack(p, 0, (cudaStream_t) stream);
 	if (rc) return fail(rc, "stack_mean launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
 	return SSC_OK;
 }
@@ -553,7 +559,7 @@ int run_job(const Job &job) {
 						if ((rc = ssc::launch_sum_finish(d.acc, (size_t) C * pc.rows * W, d.maxim, d.out, d.stream))) return fail(rc, "sum finish failed");
 					}
 				} else {
-					if ((rc = ssc::launch_stack_generic(p, nullptr, nullptr, 0, job.op == OP_MEDIAN, d.stream)))
+					if ((rc = ssc::launch_stack(p, job.op == OP_MEDIAN, d.stream)))
 						return fail(rc, "stack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 				}
 			}

@@ -241,3 +241,48 @@ def test_callbacks_and_cancel(gpu):
         assert e.value.code == -1                                       # cancelled: -1, as the reference
     finally:
         gpu.set_callbacks()
+
+
+# --------------------------------------------------------------------------- both kernels agree
+@pytest.mark.parametrize("rej", list(REJ) + ["median"])
+@pytest.mark.parametrize("n,norm", [(16, 0), (24, 3), (32, 2), (33, 1), (64, 4), (64, 0)])
+def test_register_network_kernel_equals_general_kernel(gpu, port, rej, n, norm):
+    """ssc_stack_fast.cu (register sorting network) and ssc_stack_generic.cu (shared-memory
+    columns) must be interchangeable: same image, counters and guard events, both equal to the oracle."""
+    fr = synth.make_frames(n, 1, 24, 64, seed=n + norm, outlier_p=8e-3, zero_p=2e-3, stars=3)
+    outs = []
+    for path in (0, 1):
+        gpu.set_kernel_path(path)
+        try:
+            if rej == "median":
+                res = gpu.stack_median(gpu.Sequence(fr), normalize=norm, want_coeff=True)
+            else:
+                rj, sig = REJ[rej]
+                res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), rj, sig, norm)
+        finally:
+            gpu.set_kernel_path(0)
+        outs.append(res)
+    a, b = outs
+    assert np.array_equal(a.data, b.data)
+    assert np.array_equal(a.irej, b.irej) and a.guard_fired == b.guard_fired and a.cap_hit == b.cap_hit
+    if rej == "median":
+        assert np.array_equal(a.data, port.stack_median(fr, normalize=norm, coeff=a.coeff)["out"])
+    else:
+        rj, sig = REJ[rej]
+        same = port.stack_mean(fr, rj, sig, norm, coeff=a.coeff, sd_mode=port.SD_EXACT)
+        assert np.array_equal(a.data, same["out"]) and np.array_equal(a.irej, same["irej"])
+        assert a.guard_fired == same["guard_fired"]
+
+
+def test_fast_normalization_domain_fallback(gpu, port):
+    """Coefficients outside the 2^52-trick domain (a nearly black frame against a bright reference)
+    take the conversion-based normalization: same results."""
+    fr = synth.make_frames(8, 1, 16, 32, seed=4)
+    fr[3] = (fr[3] // 1000).astype(np.uint16)               # location ~1: mul ~ 1000, still in the domain
+    fr[3][fr[3] == 0] = 1
+    fr[5] = 1                                                # constant frame: scale 0 -> inf / nan coefficients
+    for norm in (1, 2, 3, 4):
+        res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), 2, (4, 3), norm)
+        same = port.stack_mean(fr, 2, (4, 3), norm, coeff=res.coeff, sd_mode=port.SD_EXACT)
+        assert np.array_equal(res.data, same["out"]), norm
+        assert np.array_equal(res.irej, same["irej"]), norm
