@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsiril_stack_cuda.so")
+LIB_PATH = os.environ.get("SSC_LIB", os.path.join(_HERE, "libsiril_stack_cuda.so"))	# SSC_LIB: experiments only
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         "libsiril_stack_cuda.so is not built (run `python __graft_entry__.py`); "

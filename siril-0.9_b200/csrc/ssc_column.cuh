@@ -37,7 +37,7 @@ __device__ __forceinline__ double column_median(Column c, int o, int n) {
 	int lhs = (n - 1) >> 1, rhs = n >> 1;
 	unsigned int a = c.get(o + lhs);
 	if (lhs == rhs) return (double) (int) a;
-	return ddiv((double) (int) (a + c.get(o + rhs)), 2.0);
+	return dmul((double) (int) (a + c.get(o + rhs)), 0.5);	// x / 2.0 == x * 0.5 exactly
 }
 
 // One flag-and-remove pass of SIGMA / WINSORIZED (stacking.c:1680-1693, 1731-1747)
@@ -96,8 +96,11 @@ __device__ __forceinline__ int sigma_pass_sorted(Column c, int &o, int &N, doubl
 
 // stacking.c:1656-1794 for one column whose N samples are sorted ascending in
 // c[0..N) with S = sum, Q = sum of squares.  Returns the output sample.
-__device__ __forceinline__ unsigned int reject_sorted_and_mean(Column c, int N, int rejection, double slow,
-		double shigh, unsigned long long S, unsigned long long Q, RejectState &st) {
+// unbias: optional table of (double) n / (double) (n - 1) for n <= 64 (the quotient itself is
+// the reference's; looking it up saves a division per iteration).
+static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int N, int rejection, double slow,
+		double shigh, unsigned long long S, unsigned long long Q, RejectState &st,
+		const double *unbias = nullptr) {
 	double sigma, median;
 	int n, r = 0, iter = 0, o = 0;
 
@@ -125,7 +128,7 @@ __device__ __forceinline__ unsigned int reject_sorted_and_mean(Column c, int N, 
 	}
 	case SIGMA:		// stacking.c:1674-1695
 		do {
-			sigma = sd_from_sums(S, Q, N);
+			sigma = sd_from_sums(S, Q, N, unbias);
 			median = column_median(c, o, N);
 			n = sigma_pass_sorted(c, o, N, slow, shigh, sigma, median, r, S, Q, st);
 			if (++iter >= SSC_ITER_CAP) { st.cap = 1; break; }
@@ -133,7 +136,7 @@ __device__ __forceinline__ unsigned int reject_sorted_and_mean(Column c, int N, 
 		break;
 	case SIGMEDIAN:		// stacking.c:1696-1709: rejected samples become round_to_WORD(median), N stays
 		do {
-			sigma = sd_from_sums(S, Q, N);
+			sigma = sd_from_sums(S, Q, N, unbias);
 			median = column_median(c, 0, N);
 			const unsigned int m = round_to_word(median);
 			const double tl = dmul(slow, sigma), th = dmul(shigh, sigma);
@@ -166,7 +169,7 @@ __device__ __forceinline__ unsigned int reject_sorted_and_mean(Column c, int N, 
 		break;
 	case WINSORIZED:	// stacking.c:1710-1749
 		do {
-			sigma = sd_from_sums(S, Q, N);
+			sigma = sd_from_sums(S, Q, N, unbias);
 			median = column_median(c, o, N);
 			// w_stack is never materialised: clamping a sorted stack keeps it sorted and only
 			// ever rewrites a prefix (to one value) and a suffix (to one value), so
@@ -202,11 +205,11 @@ __device__ __forceinline__ unsigned int reject_sorted_and_mean(Column c, int N, 
 				}
 				const unsigned int wl = lhs < clo ? vlo : (lhs >= N - chi ? vhi : c.get(o + lhs));
 				const unsigned int wr = rhs < clo ? vlo : (rhs >= N - chi ? vhi : c.get(o + rhs));
-				median = lhs == rhs ? (double) (int) wl : ddiv((double) (int) (wl + wr), 2.0);
+				median = lhs == rhs ? (double) (int) wl : dmul((double) (int) (wl + wr), 0.5);
 				const unsigned long long Sw = Sm + (unsigned long long) clo * vlo + (unsigned long long) chi * vhi;
 				const unsigned long long Qw = Qm + (unsigned long long) clo * sq(vlo) + (unsigned long long) chi * sq(vhi);
 				sigma0 = sigma;
-				sigma = dmul(1.134, sd_from_sums(Sw, Qw, N));
+				sigma = dmul(1.134, sd_from_sums(Sw, Qw, N, unbias));
 				if (++inner >= SSC_ITER_CAP) { st.cap = 1; break; }
 			} while (ddiv(fabs(dsub(sigma, sigma0)), sigma0) > 0.0005);
 			n = sigma_pass_sorted(c, o, N, slow, shigh, sigma, median, r, S, Q, st);

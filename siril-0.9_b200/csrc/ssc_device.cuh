@@ -47,10 +47,12 @@ __device__ __forceinline__ unsigned int normalize_sample(unsigned int p, int mod
 // variance carries a single rounding; then the reference's own
 // sqrt(variance * (n / (n-1))).  GSL accumulates the same quantity in x87
 // long double, which FP64 cannot reproduce bit for bit.
-__device__ __forceinline__ double sd_from_sums(unsigned long long S, unsigned long long Q, int n) {
+__device__ __forceinline__ double sd_from_sums(unsigned long long S, unsigned long long Q, int n,
+		const double *unbias = nullptr) {
 	unsigned long long D = (unsigned long long) n * Q - S * S;
 	double var = ddiv(__ull2double_rn(D), (double) ((long long) n * n));
-	return dsqrt(dmul(var, ddiv((double) n, (double) (n - 1))));
+	double nn1 = (unbias && n <= 64) ? unbias[n] : ddiv((double) n, (double) (n - 1));
+	return dsqrt(dmul(var, nn1));
 }
 
 // sigma_clipping, stacking.c:1148-1161: -1 low, +1 high, 0 keep

@@ -19,13 +19,13 @@
 // add in round-toward-zero mode onto 1.5*2^52 (floor in the low word) and one
 // VIMNMX.RELU clamp.  Both are exact; frames whose coefficients would leave
 // the trick's domain (|value| >= 2^31) take the conversion-based form instead.
+#include <cstdlib>
 #include "ssc_column.cuh"
 #include "ssc_kernels.h"
 #include "ssc_sortnet.h"
 
 namespace ssc {
 
-constexpr int FAST_THREADS = 128;
 
 __device__ __forceinline__ double word_to_double(unsigned int p) {
 	return dsub(__hiloint2double(0x43300000, (int) p), 4503599627370496.0);	// (2^52 + p) - 2^52, exact
@@ -34,9 +34,17 @@ __device__ __forceinline__ double word_to_double(unsigned int p) {
 // round_to_WORD (utils.c:68-74) for |y| < 2^31: floor(y + 0.5) read from the low word of
 // (y + 0.5) +rz 1.5*2^52, then max(min(., 65535), 0).  Equals the reference for every such y:
 // y <= 0 -> floor <= 0 -> 0;  0 < y <= 65535 -> trunc(y + 0.5);  y > 65535 -> >= 65535 -> 65535.
+#ifndef SSC_NORM_XU_OUT
+#define SSC_NORM_XU_OUT 0
+#endif
 __device__ __forceinline__ unsigned int round_to_word_fast(double y) {
+#if SSC_NORM_XU_OUT
+	// F2I.F64.TRUNC saturates and maps NaN to 0: valid for every y, costs a conversion-unit slot
+	return (unsigned int) __vimin_s32_relu(__double2int_rz(dadd(y, 0.5)), 65535);
+#else
 	double u = __dadd_rz(dadd(y, 0.5), 6755399441055744.0);
 	return (unsigned int) __vimin_s32_relu(__double2loint(u), 65535);
+#endif
 }
 
 template <int NP>
@@ -48,21 +56,71 @@ __device__ __forceinline__ void sort_network(unsigned int (&v)[NP]) {
 #undef SSC_CE
 }
 
-template <int NP>
-__global__ void __launch_bounds__(FAST_THREADS, 4)
+// One sample pair through normalization (stacking.c:1635-1652), KIND = the reference's enum value.
+// ADDITIVE / MULTIPLICATIVE have scale == 1.0 exactly (stacking.c:130-134), and x * 1.0 == x.
+template <int KIND>
+__device__ __forceinline__ unsigned int normalize_pair_fast(unsigned int w, double off, double mul, double sc,
+		unsigned long long &Qa, unsigned long long &Qb) {
+	// I2F.F64.U16 reads either half of the packed word directly (conversion unit, off the ALU pipe)
+	double da = (double) (unsigned short) (w & 0xFFFFu), db = (double) (unsigned short) (w >> 16);
+	if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) {
+		da = dmul(da, sc);
+		db = dmul(db, sc);
+	}
+	if constexpr (KIND == ADDITIVE || KIND == ADDITIVE_SCALING) {
+		da = dsub(da, off);
+		db = dsub(db, off);
+	} else {
+		da = dmul(da, mul);
+		db = dmul(db, mul);
+	}
+	const unsigned int ra = round_to_word_fast(da), rb = round_to_word_fast(db);
+	Qa += (unsigned long long) ra * ra;	// IMAD.WIDE on the values while they are still unpacked
+	Qb += (unsigned long long) rb * rb;
+	return ra | (rb << 16);
+}
+
+template <int NP, bool FULL, int KIND>
+__device__ __forceinline__ void normalize_all(unsigned int (&v)[NP], int N, const double *s_coef,
+		unsigned long long &Qa, unsigned long long &Qb) {
+#pragma unroll
+	for (int f = 0; f < NP; f++) {
+		if (FULL || f < N) {
+			double off = 0.0, mul = 1.0, sc = 1.0;
+			if constexpr (KIND == ADDITIVE || KIND == ADDITIVE_SCALING) off = s_coef[f];
+			if constexpr (KIND == MULTIPLICATIVE || KIND == MULTIPLICATIVE_SCALING) mul = s_coef[64 + f];
+			if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) sc = s_coef[128 + f];
+			v[f] = normalize_pair_fast<KIND>(v[f], off, mul, sc, Qa, Qb);
+		}
+	}
+}
+
+// FULL: n_frames == NP (no sentinel padding, no per-frame bound checks in the unrolled code)
+#ifndef SSC_FAST_RESIDENT_THREADS
+#define SSC_FAST_RESIDENT_THREADS 512	// threads per SM the register budget is sized for
+#endif
+template <int NP, bool FULL, int FAST_THREADS>
+__global__ void __launch_bounds__(FAST_THREADS, SSC_FAST_RESIDENT_THREADS / FAST_THREADS)
 k_stack_fast(StackParams p, int is_median) {
-	extern __shared__ unsigned int cols[];		// [NP][FAST_THREADS] packed sorted columns
+	extern __shared__ unsigned int cols[];		// [NP][FAST_THREADS] packed columns
 	__shared__ double s_coef[3 * 64];
+	__shared__ double s_unbias[65];			// (double) n / (double) (n - 1), the reference's own quotient
 	__shared__ int s_fast_norm;
 	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
+	__shared__ unsigned int s_qcount;			// work queue of pixels whose first pass rejects something
+	__shared__ unsigned short s_qitem[2 * FAST_THREADS], s_res[2 * FAST_THREADS];
+	__shared__ unsigned char s_layer[FAST_THREADS];
+	__shared__ unsigned int s_S[2 * FAST_THREADS];
+	__shared__ unsigned long long s_Q[2 * FAST_THREADS];
 
 	const ssc_band &b = p.band;
-	const int W = b.width, N = b.n_frames, tid = threadIdx.x;
+	const int W = b.width, N = FULL ? NP : b.n_frames, tid = threadIdx.x;
 	const int W2 = W >> 1;
 	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
 
 	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
 	if (tid == 0) s_fast_norm = 1;
+	if (tid >= 2 && tid <= 64) s_unbias[tid] = ddiv((double) tid, (double) (tid - 1));
 	__syncthreads();
 	if (norm && tid < N) {
 		const double off = p.coeff[tid], mul = p.coeff[N + tid], sc = p.coeff[2 * N + tid];
@@ -85,97 +143,172 @@ k_stack_fast(StackParams p, int is_median) {
 	const int layer = (int) (g / ((unsigned long long) W2 * b.out_rows));
 	const int R = b.out_row0 + rr;				// result storage row (stacking.c:731,1600)
 	const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - R : R;
-	const unsigned int *src = reinterpret_cast<const unsigned int *>(
-			b.frames + (size_t) layer * b.layer_stride + (size_t) (srow - b.buf_row0) * W) + x2;
+	// per-thread offset inside a frame (32 bits: a frame holds < 2^32 pixel pairs) on top of a
+	// block-uniform per-frame base, so the 64 address computations stay off the ALU pipe
+	const unsigned int toff = (unsigned int) ((((size_t) layer * b.layer_stride + (size_t) (srow - b.buf_row0) * W) >> 1) + x2);
+	const unsigned int *frames32 = reinterpret_cast<const unsigned int *>(b.frames);
 	const size_t fstride2 = b.frame_stride >> 1;
 
 	// ---- gather: one packed load per frame, all issued before first use ----
 	unsigned int v[NP];
+	const char *ptr = reinterpret_cast<const char *>(frames32 + toff);
+	const size_t fstride_bytes = fstride2 * sizeof(unsigned int);
 #pragma unroll
-	for (int f = 0; f < NP; f++)
-		v[f] = f < N ? __ldg(src + (size_t) f * fstride2) : 0xFFFFFFFFu;
+	for (int f = 0; f < NP; f++) {
+		v[f] = (FULL || f < N) ? __ldg(reinterpret_cast<const unsigned int *>(ptr)) : 0xFFFFFFFFu;
+		ptr += fstride_bytes;
+	}
 
-	// ---- normalize (stacking.c:1635-1652; median path :750-764) and exact sums ----
-	unsigned long long Sa = 0, Sb = 0, Qa = 0, Qb = 0;
+	// ---- normalize (stacking.c:1635-1652; median path :750-764) ----
+	unsigned long long Qa = 0, Qb = 0;	// exact sums of squares of the (normalized) samples
+	bool have_q = false;
 	if (norm) {
-		const bool fast = s_fast_norm != 0;
-		const int mode = p.normalize;
-#pragma unroll
-		for (int f = 0; f < NP; f++) {
-			if (f < N) {
-				unsigned int pa = v[f] & 0xFFFFu, pb = v[f] >> 16;
-				const double off = s_coef[f], mul = s_coef[64 + f], sc = s_coef[128 + f];
-				if (fast) {
-					double da = word_to_double(pa), db = word_to_double(pb);
-					if (mode == ADDITIVE_SCALING || mode == MULTIPLICATIVE_SCALING) {
-						da = dmul(da, sc);
-						db = dmul(db, sc);
-					}		// ADDITIVE / MULTIPLICATIVE: scale is exactly 1.0, x * 1.0 == x
-					if (mode == ADDITIVE || mode == ADDITIVE_SCALING) {
-						da = dsub(da, off);
-						db = dsub(db, off);
-					} else {
-						da = dmul(da, mul);
-						db = dmul(db, mul);
-					}
-					pa = round_to_word_fast(da);
-					pb = round_to_word_fast(db);
-				} else {
-					pa = normalize_sample(pa, mode, off, mul, sc);
-					pb = normalize_sample(pb, mode, off, mul, sc);
-				}
-				Sa += pa; Sb += pb; Qa += sq(pa); Qb += sq(pb);
-				v[f] = pa | (pb << 16);
+		if (s_fast_norm) {
+			have_q = true;
+			switch (p.normalize) {
+			case ADDITIVE: normalize_all<NP, FULL, ADDITIVE>(v, N, s_coef, Qa, Qb); break;
+			case MULTIPLICATIVE: normalize_all<NP, FULL, MULTIPLICATIVE>(v, N, s_coef, Qa, Qb); break;
+			case ADDITIVE_SCALING: normalize_all<NP, FULL, ADDITIVE_SCALING>(v, N, s_coef, Qa, Qb); break;
+			default: normalize_all<NP, FULL, MULTIPLICATIVE_SCALING>(v, N, s_coef, Qa, Qb); break;
 			}
-		}
-	} else {
+		} else {
+			// coefficients outside the tricks' domain: conversion-based form, rolled loop over the
+			// shared-memory copy (rare: keep it out of the straight-line code)
 #pragma unroll
-		for (int f = 0; f < NP; f++) {
-			if (f < N) {
-				unsigned int pa = v[f] & 0xFFFFu, pb = v[f] >> 16;
-				Sa += pa; Sb += pb; Qa += sq(pa); Qb += sq(pb);
+			for (int f = 0; f < NP; f++) cols[f * FAST_THREADS + tid] = v[f];
+			for (int f = 0; f < N; f++) {
+				unsigned int w = cols[f * FAST_THREADS + tid];
+				unsigned int pa = normalize_sample(w & 0xFFFFu, p.normalize, s_coef[f], s_coef[64 + f], s_coef[128 + f]);
+				unsigned int pb = normalize_sample(w >> 16, p.normalize, s_coef[f], s_coef[64 + f], s_coef[128 + f]);
+				cols[f * FAST_THREADS + tid] = pa | (pb << 16);
 			}
+#pragma unroll
+			for (int f = 0; f < NP; f++) v[f] = cols[f * FAST_THREADS + tid];
 		}
 	}
 
-	unsigned int ra, rb;
-	RejectState sta{0, 0, 0, 0}, stb{0, 0, 0, 0};
-	if (!is_median && p.rejection == NO_REJEC) {
-		// stacking.c:1790-1794 with nothing rejected: no ordering needed at all
-		ra = round_to_word(ddiv((double) (long long) Sa, (double) N));
-		rb = round_to_word(ddiv((double) (long long) Sb, (double) N));
-	} else {
+	unsigned int res[2];
+	if (is_median) {
 		sort_network<NP>(v);			// sentinels (0xFFFF) sort behind the N samples
-		if (is_median && N == NP) {		// stacking.c:765-767: truncating median, straight from registers
-			unsigned int lo = v[NP / 2 - 1], hi = v[NP / 2];
-			ra = ((lo & 0xFFFFu) + (hi & 0xFFFFu)) >> 1;
-			rb = ((lo >> 16) + (hi >> 16)) >> 1;
+		if (FULL) {				// stacking.c:765-767: truncating median, straight from registers
+			const unsigned int lo = v[NP / 2 - 1], hi = v[NP / 2];
+			res[0] = ((lo & 0xFFFFu) + (hi & 0xFFFFu)) >> 1;
+			res[1] = ((lo >> 16) + (hi >> 16)) >> 1;
 		} else {
 #pragma unroll
-			for (int f = 0; f < NP; f++)
-				if (f < N) cols[f * FAST_THREADS + tid] = v[f];
-			Column ca{reinterpret_cast<WORD *>(cols) + 2 * tid, 2 * FAST_THREADS};
-			Column cb{reinterpret_cast<WORD *>(cols) + 2 * tid + 1, 2 * FAST_THREADS};
-			if (is_median) {
-				const int lhs = (N - 1) >> 1, rhs = N >> 1;
-				ra = (ca.get(lhs) + ca.get(rhs)) >> 1;
-				rb = (cb.get(lhs) + cb.get(rhs)) >> 1;
-			} else {
-				ra = reject_sorted_and_mean(ca, N, p.rejection, p.sig_low, p.sig_high, Sa, Qa, sta);
-				rb = reject_sorted_and_mean(cb, N, p.rejection, p.sig_low, p.sig_high, Sb, Qb, stb);
+			for (int f = 0; f < NP; f++) cols[f * FAST_THREADS + tid] = v[f];
+			const int lhs = (N - 1) >> 1, rhs = N >> 1;
+			const unsigned int lo = cols[lhs * FAST_THREADS + tid], hi = cols[rhs * FAST_THREADS + tid];
+			res[0] = ((lo & 0xFFFFu) + (hi & 0xFFFFu)) >> 1;
+			res[1] = ((lo >> 16) + (hi >> 16)) >> 1;
+		}
+	} else {
+		// exact integer sums of the (normalized) samples; the sum fits 32 bits and comes straight
+		// from the packed words (IDP.2A: acc + lo16 * 1 + hi16 * 0), the sum of squares needs 64
+		unsigned int Sa = 0, Sb = 0;
+#pragma unroll
+		for (int f = 0; f < NP; f++) {
+			if (FULL || f < N) {
+				Sa = __dp2a_lo(v[f], 0x0001u, Sa);
+				Sb = __dp2a_lo(v[f], 0x0100u, Sb);
 			}
+		}
+		if (!have_q) {
+#pragma unroll
+			for (int f = 0; f < NP; f++) {
+				if (FULL || f < N) {
+					const unsigned int pa = v[f] & 0xFFFFu, pb = v[f] >> 16;
+					Qa += (unsigned long long) pa * pa;
+					Qb += (unsigned long long) pb * pb;
+				}
+			}
+		}
+		const unsigned long long S[2] = {Sa, Sb}, Q[2] = {Qa, Qb};
+		if (p.rejection == NO_REJEC) {
+			// stacking.c:1790-1794 with nothing rejected: no ordering needed at all
+			res[0] = round_to_word(ddiv((double) (long long) S[0], (double) N));
+			res[1] = round_to_word(ddiv((double) (long long) S[1], (double) N));
+		} else {
+			sort_network<NP>(v);
+#pragma unroll
+			for (int f = 0; f < NP; f++)
+				if (FULL || f < N) cols[f * FAST_THREADS + tid] = v[f];
+			WORD *cols16 = reinterpret_cast<WORD *>(cols);
+
+			// ---- phase 1: can the first pass flag anything at all?  Flags are monotone in the
+			// sample value (low flags a prefix, high flags a suffix of the sorted stack), so when
+			// neither the smallest nor the largest sample is flagged nothing is, the reference's
+			// do-while ends after one pass (n == 0) and the result is the plain mean.  Both pixels
+			// are evaluated side by side from registers; only the others go to the work queue.
+			// (with N <= 4 the reference's "N - r <= 4" break is taken at the very first sample:
+			// that pixel must go through the full pass so that the event is counted)
+			const bool quick = (p.rejection == SIGMA && N > 4) || p.rejection == SIGMEDIAN || p.rejection == PERCENTILE;
+			const unsigned int lo_w = v[0];
+			const unsigned int hi_w = FULL ? v[NP - 1] : cols[(N - 1) * FAST_THREADS + tid];
+			const unsigned int ml_w = FULL ? v[(NP - 1) / 2] : cols[((N - 1) >> 1) * FAST_THREADS + tid];
+			const unsigned int mr_w = FULL ? v[NP / 2] : cols[(N >> 1) * FAST_THREADS + tid];
+			bool pending[2];
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				const unsigned int lo = h ? lo_w >> 16 : lo_w & 0xFFFFu, hi = h ? hi_w >> 16 : hi_w & 0xFFFFu;
+				const unsigned int ml = h ? ml_w >> 16 : ml_w & 0xFFFFu, mr = h ? mr_w >> 16 : mr_w & 0xFFFFu;
+				const double median = (N & 1) ? (double) (int) ml : dmul((double) (int) (ml + mr), 0.5);
+				bool flagged = true;
+				if (quick) {
+					if (p.rejection == PERCENTILE) {
+						flagged = clip_percentile(lo, p.sig_low, p.sig_high, median) != 0
+								|| clip_percentile(hi, p.sig_low, p.sig_high, median) != 0;
+					} else {
+						const double sigma = sd_from_sums(S[h], Q[h], N, s_unbias);
+						flagged = clip_sigma(lo, p.sig_low, p.sig_high, sigma, median) != 0
+								|| clip_sigma(hi, p.sig_low, p.sig_high, sigma, median) != 0;
+					}
+				}
+				pending[h] = flagged && active;	// padding threads of the last block own no pixel
+				res[h] = round_to_word(ddiv((double) (long long) S[h], (double) N));
+			}
+			if (tid == 0) s_qcount = 0;
+			s_layer[tid] = (unsigned char) layer;
+			__syncthreads();
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				if (pending[h]) {
+					const unsigned int slot = atomicAdd(&s_qcount, 1u);
+					s_qitem[slot] = (unsigned short) (2 * tid + h);
+					s_S[2 * tid + h] = (unsigned int) S[h];
+					s_Q[2 * tid + h] = Q[h];
+				}
+			}
+			__syncthreads();
+
+			// ---- phase 2: the pending pixels, spread over all warps of the block (their sorted
+			// columns sit in shared memory, any thread can run them) ----
+			const unsigned int n_items = s_qcount;
+			constexpr int NWARPS = FAST_THREADS / 32;
+			(void) NWARPS;
+			for (unsigned int i = tid; i < n_items; i += FAST_THREADS) {	// dense: full warps run the heavy code
+				const unsigned int item = s_qitem[i];
+				Column c{cols16 + item, 2 * FAST_THREADS};
+				RejectState ist{0, 0, 0, 0};
+				const unsigned int r = reject_sorted_and_mean(c, N, p.rejection, p.sig_low, p.sig_high,
+						s_S[item], s_Q[item], ist, s_unbias);
+				s_res[item] = (unsigned short) r;
+				const int il = s_layer[item >> 1];
+				if (ist.rej_lo) atomicAdd(&blk_counters[il * 2 + 0], (unsigned long long) ist.rej_lo);
+				if (ist.rej_hi) atomicAdd(&blk_counters[il * 2 + 1], (unsigned long long) ist.rej_hi);
+				if (ist.guard) atomicAdd(&blk_counters[6], 1ull);
+				if (ist.cap) atomicAdd(&blk_counters[7], 1ull);
+			}
+			__syncthreads();
+			if (pending[0]) res[0] = s_res[2 * tid];
+			if (pending[1]) res[1] = s_res[2 * tid + 1];
 		}
 	}
 
 	if (active) {
 		unsigned int *dst = reinterpret_cast<unsigned int *>(
 				p.out + (size_t) layer * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W) + x2;
-		*dst = ra | (rb << 16);
-		const unsigned int rl = sta.rej_lo + stb.rej_lo, rh = sta.rej_hi + stb.rej_hi;
-		if (rl) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) rl);
-		if (rh) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) rh);
-		if (sta.guard + stb.guard) atomicAdd(&blk_counters[6], (unsigned long long) (sta.guard + stb.guard));
-		if (sta.cap + stb.cap) atomicAdd(&blk_counters[7], (unsigned long long) (sta.cap + stb.cap));
+		*dst = res[0] | (res[1] << 16);
 	}
 	__syncthreads();
 	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
@@ -193,17 +326,39 @@ bool fast_path_eligible(const StackParams &p, int is_median) {
 	return true;
 }
 
-template <int NP>
-static int launch_fast_np(const StackParams &p, int is_median, cudaStream_t stream) {
+// Threads per block: more warps of one block per scheduler run the same straight-line code
+// close together and share instruction fetches (SSC_FAST_TPB overrides, for experiments).
+static int fast_threads() {
+	static int tpb = 0;
+	if (!tpb) {
+		const char *e = getenv("SSC_FAST_TPB");
+		tpb = e ? atoi(e) : 256;
+		if (tpb != 128 && tpb != 256 && tpb != 512) tpb = 256;
+	}
+	return tpb;
+}
+
+template <int NP, bool FULL, int TPB>
+static int launch_fast_cfg(const StackParams &p, int is_median, cudaStream_t stream) {
 	const ssc_band &b = p.band;
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * (b.width >> 1);
 	if (total == 0) return SSC_OK;
-	const size_t smem = (size_t) NP * FAST_THREADS * sizeof(unsigned int);
-	if (cudaFuncSetAttribute(k_stack_fast<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
+	const size_t smem = (size_t) NP * TPB * sizeof(unsigned int);
+	if (cudaFuncSetAttribute(k_stack_fast<NP, FULL, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
-	const unsigned int grid = (unsigned int) ((total + FAST_THREADS - 1) / FAST_THREADS);
-	k_stack_fast<NP><<<grid, FAST_THREADS, smem, stream>>>(p, is_median);
+	const unsigned int grid = (unsigned int) ((total + TPB - 1) / TPB);
+	k_stack_fast<NP, FULL, TPB><<<grid, TPB, smem, stream>>>(p, is_median);
 	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
+}
+
+template <int NP>
+static int launch_fast_np(const StackParams &p, int is_median, cudaStream_t stream) {
+	const bool full = p.band.n_frames == NP;
+	switch (fast_threads()) {
+	case 128: return full ? launch_fast_cfg<NP, true, 128>(p, is_median, stream) : launch_fast_cfg<NP, false, 128>(p, is_median, stream);
+	case 512: return full ? launch_fast_cfg<NP, true, 512>(p, is_median, stream) : launch_fast_cfg<NP, false, 512>(p, is_median, stream);
+	default: return full ? launch_fast_cfg<NP, true, 256>(p, is_median, stream) : launch_fast_cfg<NP, false, 256>(p, is_median, stream);
+	}
 }
 
 int launch_stack_fast(const StackParams &p, int is_median, cudaStream_t stream) {

@@ -275,14 +275,15 @@ def test_register_network_kernel_equals_general_kernel(gpu, port, rej, n, norm):
 
 
 def test_fast_normalization_domain_fallback(gpu, port):
-    """Coefficients outside the 2^52-trick domain (a nearly black frame against a bright reference)
-    take the conversion-based normalization: same results."""
-    fr = synth.make_frames(8, 1, 16, 32, seed=4)
-    fr[3] = (fr[3] // 1000).astype(np.uint16)               # location ~1: mul ~ 1000, still in the domain
-    fr[3][fr[3] == 0] = 1
-    fr[5] = 1                                                # constant frame: scale 0 -> inf / nan coefficients
+    """Coefficients outside the domain of the 2^52 conversion tricks (a nearly black frame against a
+    bright reference: mul ~ 5e4, products beyond 2^31) take the conversion-based normalization."""
+    rng = np.random.default_rng(4)
+    fr = rng.normal(50000, 300, size=(8, 1, 16, 32)).clip(0, 65535).astype(np.uint16)
+    fr[3] = rng.integers(1, 4, size=(1, 16, 32)).astype(np.uint16)      # location ~2: mul ~ 25000
+    fr[3, 0, 2, :8] = 60000                                             # 60000 * 25000 > 2^31
     for norm in (1, 2, 3, 4):
         res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), 2, (4, 3), norm)
+        assert np.isfinite(res.coeff).all()
         same = port.stack_mean(fr, 2, (4, 3), norm, coeff=res.coeff, sd_mode=port.SD_EXACT)
         assert np.array_equal(res.data, same["out"]), norm
         assert np.array_equal(res.irej, same["irej"]), norm
