@@ -1,0 +1,140 @@
+"""Device layer (ssc_dev_*) on caller-owned device memory: band decomposition invariance (the
+multi-GPU path run on one GPU, band by band), and properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def dev_u16(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int16)).cuda()
+
+
+def host_u16(t):
+    return t.cpu().numpy().view(np.uint16)
+
+
+def run_pipeline(gpu, frames_dev, n, c, h, w, bands, rejection, sig, normalize, median=False):
+    """The per-rank sequence of bench.py, band by band on one GPU; histograms add up across bands."""
+    sp = torch.cuda.current_stream().cuda_stream
+    out = torch.zeros((c, h, w), dtype=torch.int16, device="cuda")
+    hist = torch.zeros((n, gpu.HIST_STRIDE), dtype=torch.int32, device="cuda")
+    scratch = torch.empty((n, 65536), dtype=torch.int32, device="cuda")
+    stats = torch.empty((4, n), dtype=torch.float64, device="cuda")
+    coeff = torch.empty((3, n), dtype=torch.float64, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    counters = torch.zeros(gpu.N_COUNTERS, dtype=torch.int64, device="cuda")
+    mk = lambda r0, rn: gpu.dev.band(frames_dev.data_ptr(), n, c, h, w, out_row0=r0, out_rows=rn)
+    if normalize:
+        for r0, rn in bands:
+            gpu.dev.histogram(mk(r0, rn), hist.data_ptr(), sp)
+        gpu.dev.ikss(hist.data_ptr(), n, stats.data_ptr(), scratch.data_ptr(), sp)
+        gpu.dev.norm_coeffs(stats.data_ptr(), n, 0, normalize, coeff.data_ptr(), status.data_ptr(), sp)
+    for r0, rn in bands:
+        if median:
+            gpu.dev.stack_median(mk(r0, rn), out.data_ptr(), normalize, coeff.data_ptr(), out_layer_stride=h * w,
+                                 out_buf_row0=0, stream=sp)
+        else:
+            gpu.dev.stack_mean(mk(r0, rn), out.data_ptr(), counters.data_ptr(), rejection, sig, normalize,
+                               coeff.data_ptr(), out_layer_stride=h * w, out_buf_row0=0, stream=sp)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    return host_u16(out), counters.cpu().numpy(), coeff.cpu().numpy()
+
+
+@pytest.mark.parametrize("rej,sig", [(2, (4.0, 3.0)), (4, (4.0, 3.0)), (5, (5.0, 2.5))])
+def test_band_decomposition_is_invariant(gpu, port, rej, sig):
+    n, c, h, w = 24, 3, 45, 64
+    fr = synth.make_frames(n, c, h, w, seed=31, outlier_p=5e-3, zero_p=1e-3, stars=4)
+    d = dev_u16(fr)
+    whole = run_pipeline(gpu, d, n, c, h, w, [(0, h)], rej, sig, 3)
+    for bands in ([(0, 23), (23, 22)], [(0, 6), (6, 6), (12, 6), (18, 6), (24, 6), (30, 5), (35, 5), (40, 5)]):
+        part = run_pipeline(gpu, d, n, c, h, w, bands, rej, sig, 3)
+        assert np.array_equal(part[0], whole[0])
+        assert np.array_equal(part[1], whole[1])
+        assert np.array_equal(part[2], whole[2])                        # statistics exact under sharding
+    ref = port.stack_mean(fr, rej, sig, 3, coeff=whole[2], sd_mode=port.SD_EXACT)
+    assert np.array_equal(whole[0], ref["out"])
+    assert np.array_equal(whole[1][:6].reshape(3, 2), ref["irej"].astype(np.int64))
+
+
+def test_synthetic_generator_is_band_independent(gpu):
+    n, c, h, w = 3, 3, 64, 96
+    sp = torch.cuda.current_stream().cuda_stream
+    full = torch.empty((n, c, h, w), dtype=torch.int16, device="cuda")
+    gpu.dev.synth_frames(full.data_ptr(), n, c, h, w, 0, 0, h, 0, 1234, sp)
+    part = torch.empty((n, c, 20, w), dtype=torch.int16, device="cuda")
+    gpu.dev.synth_frames(part.data_ptr(), n, c, 20, w, 0, 17, h, 0, 1234, sp)
+    torch.cuda.synchronize()
+    assert torch.equal(full[:, :, 17:37, :], part)
+    later = torch.empty((1, c, h, w), dtype=torch.int16, device="cuda")
+    gpu.dev.synth_frames(later.data_ptr(), 1, c, h, w, 2, 0, h, 0, 1234, sp)
+    torch.cuda.synchronize()
+    assert torch.equal(full[2:3], later)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes, checked through size-independent properties
+# ---------------------------------------------------------------------------------------------
+def test_cfg2_median_full_size(gpu):
+    """configs[1]: median of 32 x 4096x4096 mono.  Independent check: torch.sort along the frame
+    axis on the same device buffer, floor((s[15] + s[16]) / 2) (D7)."""
+    n, c, h, w = 32, 1, 4096, 4096
+    sp = torch.cuda.current_stream().cuda_stream
+    fr = torch.empty((n, c, h, w), dtype=torch.int16, device="cuda")
+    gpu.dev.synth_frames(fr.data_ptr(), n, c, h, w, 0, 0, h, 0, 0x5349524C, sp)
+    out = torch.empty((c, h, w), dtype=torch.int16, device="cuda")
+    gpu.dev.stack_median(gpu.dev.band(fr.data_ptr(), n, c, h, w), out.data_ptr(), stream=sp)
+    torch.cuda.synchronize()
+    got = out.view(-1).to(torch.int32) & 0xFFFF
+    x = (fr.view(n, -1).to(torch.int32) & 0xFFFF)
+    step = 4096 * 512                                                   # sort in slabs to bound memory
+    for i in range(0, x.shape[1], step):
+        s = torch.sort(x[:, i:i + step], dim=0).values
+        assert torch.equal((s[15] + s[16]) // 2, got[i:i + step])
+
+
+def test_cfg1_sum_full_size(gpu):
+    """configs[0]: sum of 16 x 1024x1024 mono; independent check in torch int64 (+ pixel 0 quirk, rescale)."""
+    n, c, h, w = 16, 1, 1024, 1024
+    sp = torch.cuda.current_stream().cuda_stream
+    fr = torch.empty((n, c, h, w), dtype=torch.int16, device="cuda")
+    gpu.dev.synth_frames(fr.data_ptr(), n, c, h, w, 0, 0, h, 0, 0x5349524C, sp)
+    acc = torch.empty((c, h, w), dtype=torch.int32, device="cuda")
+    mx = torch.zeros(1, dtype=torch.int64, device="cuda")
+    out = torch.empty((c, h, w), dtype=torch.int16, device="cuda")
+    gpu.dev.sum_accumulate(gpu.dev.band(fr.data_ptr(), n, c, h, w), acc.data_ptr(), mx.data_ptr(), sp)
+    gpu.dev.sum_finish(acc.data_ptr(), c * h * w, mx.data_ptr(), out.data_ptr(), sp)
+    torch.cuda.synchronize()
+    s = (fr.to(torch.int64) & 0xFFFF).sum(0).view(-1)
+    s[0] = 0
+    m = int(s.max())
+    assert int(mx.item()) == m and m > 65535
+    expect = torch.floor(s.to(torch.float64) * (65535.0 / m) + 0.5).clamp(0, 65535).to(torch.int64)
+    assert torch.equal(expect, out.view(-1).to(torch.int64) & 0xFFFF)
+
+
+def test_cfg3_sigma_full_width_rows_against_oracle(gpu, port):
+    """configs[2] shape per row (64 RGB frames, 6000 px wide, sigma clip, multiplicative
+    normalization) on a 96-row slab; 12 full rows are replayed through the oracle."""
+    n, c, h, w = 64, 3, 96, 6000
+    sp = torch.cuda.current_stream().cuda_stream
+    fr = torch.empty((n, c, h, w), dtype=torch.int16, device="cuda")
+    gpu.dev.synth_frames(fr.data_ptr(), n, c, h, w, 0, 1000, 4000, 0, 0x5349524C, sp)
+    out, counters, coeff = run_pipeline(gpu, fr, n, c, h, w, [(0, h)], 2, (4.0, 3.0), 2)
+    rows = list(range(0, h, 8))
+    sub = host_u16(fr[:, :, rows, :].contiguous())
+    same = port.stack_mean(sub, 2, (4.0, 3.0), 2, coeff=coeff, sd_mode=port.SD_EXACT)
+    assert np.array_equal(out[:, rows, :], same["out"])
+    gsl = port.stack_mean(sub, 2, (4.0, 3.0), 2, coeff=coeff, sd_mode=port.SD_GSL)
+    d = np.abs(out[:, rows, :].astype(np.int32) - gsl["out"].astype(np.int32))
+    assert d.max() <= 1 and (d != 0).mean() <= 1e-4                    # the bar of BASELINE.json
+    assert np.array_equal(same["irej"], gsl["irej"])
+    assert counters[6] == 0 and counters[7] == 0                       # no guard event, no iteration cap
+    # idempotence-type property at this size: stacking 64 copies of one frame returns that frame
+    one = fr[:1].expand(n, c, h, w).contiguous()
+    out1, cnt1, _ = run_pipeline(gpu, one, n, c, h, w, [(0, h)], 2, (4.0, 3.0), 0)
+    assert np.array_equal(out1, host_u16(fr[0])) and cnt1[:6].sum() == 0
