@@ -175,6 +175,10 @@ int ssc_stack_mean_with_rejection(struct stacking_args *args);
 /* compute_normalization (stacking.c:125): fills coeff->offset/mul/scale[nb_images_to_stack] */
 int ssc_compute_normalization(struct stacking_args *args, norm_coeff *coeff, normalization mode);
 
+/* The operator layer keeps its device buffers (and a pinned bounce buffer for the result)
+ * between calls; this returns them to the driver. */
+int ssc_release_workspace(void);
+
 /* Device selection for the operator layer: the operators split the image in row
  * bands over these devices (default: device 0 only). */
 int ssc_set_devices(const int *device_ids, int count);

@@ -121,7 +121,7 @@ class Callbacks(C.Structure):
 
 # every symbol include/siril_stack_cuda.h declares
 EXPORTS = [
-    "ssc_bind_sequence", "ssc_unbind_sequence", "ssc_set_callbacks", "ssc_take_result",
+    "ssc_bind_sequence", "ssc_unbind_sequence", "ssc_set_callbacks", "ssc_take_result", "ssc_release_workspace",
     "ssc_stack_summing", "ssc_stack_median", "ssc_stack_mean_with_rejection",
     "ssc_compute_normalization", "ssc_set_devices", "ssc_device_count", "ssc_set_kernel_path", "ssc_last_error",
     "ssc_version", "ssc_dev_stack_median", "ssc_dev_stack_mean", "ssc_dev_sum_accumulate",
@@ -172,6 +172,10 @@ def set_kernel_path(mode):
     rc = _lib.ssc_set_kernel_path(int(mode))
     if rc:
         raise StackError(rc, "ssc_set_kernel_path")
+
+
+def release_workspace():
+    _lib.ssc_release_workspace()
 
 
 def set_devices(ids):
@@ -252,9 +256,9 @@ class StackResult:
     def __init__(self, r, coeff=None):
         c, h, w = int(r.naxes[2]), int(r.ry), int(r.rx)
         n = c * h * w
+        self._ptr = r.data			# ownership was passed to us, as with gfit.data: freed in __del__
         buf = (C.c_uint16 * n).from_address(r.data)
-        self.data = np.frombuffer(buf, dtype=np.uint16).reshape(c, h, w).copy()
-        _libc.free(r.data)	# ownership was passed to us, as with gfit.data
+        self.data = np.frombuffer(buf, dtype=np.uint16).reshape(c, h, w)
         self.exposure = r.exposure
         self.hi = int(r.hi)
         self.irej = np.array([[r.irej[i][0], r.irej[i][1]] for i in range(3)], dtype=np.uint64)
@@ -263,6 +267,12 @@ class StackResult:
         self.t_h2d_ms, self.t_device_ms = r.t_h2d_ms, r.t_device_ms
         self.t_d2h_ms, self.t_total_ms = r.t_d2h_ms, r.t_total_ms
         self.coeff = coeff
+
+    def __del__(self):
+        if getattr(self, "_ptr", None):
+            self.data = None
+            _libc.free(self._ptr)
+            self._ptr = None
 
 
 def _filter_all(seq, nb_img, any_):

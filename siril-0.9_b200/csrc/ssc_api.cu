@@ -11,6 +11,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ssc_kernels.h"
@@ -257,10 +258,40 @@ struct Job {
 
 struct Piece { int row0, rows; };	// result storage rows
 
+// Device buffers are kept between operator calls (a 9 GB cudaMalloc/cudaFree pair costs far more
+// than the stack itself); ssc_release_workspace() returns them.
+struct Buf {
+	void *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return SSC_OK;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		if (cudaMalloc(&p, bytes) != cudaSuccess) return SSC_ERR_CUDA;
+		cap = bytes;
+		return SSC_OK;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DevCache {
+	cudaStream_t stream = nullptr;
+	Buf frames, out, hist, scratch, acc, stats, coeff, status, shifts, counters, maxim;
+	void release() {
+		Buf *all[] = {&frames, &out, &hist, &scratch, &acc, &stats, &coeff, &status, &shifts, &counters, &maxim};
+		for (Buf *b : all) b->release();
+		if (stream) cudaStreamDestroy(stream);
+		stream = nullptr;
+	}
+};
+std::map<int, DevCache> g_cache;	// by device id; operator calls are serialised (g_op_mu)
+std::mutex g_op_mu;
+void *g_pinned = nullptr;		// pinned bounce buffer for the result rows
+size_t g_pinned_cap = 0;
+
 struct Dev {
 	int id = 0;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	std::vector<Piece> pieces;
 	int max_rows = 0, max_buf_rows = 0;
 	WORD *frames = nullptr, *out = nullptr;
@@ -269,18 +300,6 @@ struct Dev {
 	int *status = nullptr, *shifts = nullptr;
 	unsigned long long *counters = nullptr, *maxim = nullptr;
 	bool resident = false;
-	void release() {
-		cudaSetDevice(id);
-		cudaFree(frames); cudaFree(out); cudaFree(hist); cudaFree(scratch); cudaFree(acc);
-		cudaFree(stats); cudaFree(coeff); cudaFree(status); cudaFree(shifts); cudaFree(counters); cudaFree(maxim);
-		for (auto &e : ev) if (e) cudaEventDestroy(e);
-		if (stream) cudaStreamDestroy(stream);
-	}
-};
-
-struct DevGuard {
-	std::vector<Dev> &devs;
-	~DevGuard() { for (auto &d : devs) d.release(); }
 };
 
 // the source storage rows a piece needs: its own rows plus the reach of the y shifts
@@ -357,7 +376,7 @@ int run_job(const Job &job) {
 	if ((int) ids.size() > H) ids.resize(H);
 	const int G = (int) ids.size();
 	std::vector<Dev> devs(G);
-	DevGuard guard{devs};
+	std::lock_guard<std::mutex> op_lock(g_op_mu);	// one operator call in flight (as in Siril: com.run_thread)
 
 	// --- plan: contiguous row bands per device (remainder rows to the first ones, as
 	// stacking.c:620-625 does), each split further if the frames do not fit in HBM ---
@@ -369,6 +388,11 @@ int run_job(const Job &job) {
 		CU(cudaSetDevice(d.id));
 		size_t free_b = 0, total_b = 0;
 		CU(cudaMemGetInfo(&free_b, &total_b));
+		{
+			auto it = g_cache.find(d.id);	// what this library already holds on the device is reusable
+			if (it != g_cache.end()) free_b += it->second.frames.cap + it->second.out.cap + it->second.hist.cap
+					+ it->second.scratch.cap + it->second.acc.cap;
+		}
 		const size_t fixed = (size_t) N * (SSC_HIST_STRIDE + 65536) * 4 + (64u << 20);
 		const size_t budget = free_b > fixed ? (size_t) ((free_b - fixed) * 0.85) : 0;
 		const size_t per_row = (size_t) N * C * W * sizeof(WORD) + (size_t) C * W * (sizeof(WORD) + sizeof(uint32_t));
@@ -387,25 +411,32 @@ int run_job(const Job &job) {
 			d.max_rows = std::max(d.max_rows, pc.rows);
 			d.max_buf_rows = std::max(d.max_buf_rows, br);
 		}
-		CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-		for (auto &e : d.ev) CU(cudaEventCreate(&e));
-		CU(cudaMalloc(&d.frames, (size_t) N * C * d.max_buf_rows * W * sizeof(WORD)));
-		CU(cudaMalloc(&d.out, (size_t) C * d.max_rows * W * sizeof(WORD)));
-		CU(cudaMalloc(&d.counters, SSC_COUNTERS * sizeof(unsigned long long)));
+		DevCache &dc = g_cache[d.id];
+		if (!dc.stream) CU(cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking));
+		d.stream = dc.stream;
+#define SSC_ENSURE(buf, bytes) do { if (dc.buf.ensure(bytes)) return fail(SSC_ERR_CUDA, "device allocation of %zu bytes failed", (size_t) (bytes)); } while (0)
+		SSC_ENSURE(frames, (size_t) N * C * d.max_buf_rows * W * sizeof(WORD));
+		SSC_ENSURE(out, (size_t) C * d.max_rows * W * sizeof(WORD));
+		SSC_ENSURE(counters, SSC_COUNTERS * sizeof(unsigned long long));
+		SSC_ENSURE(coeff, (size_t) 3 * N * sizeof(double));
+		d.frames = (WORD *) dc.frames.p; d.out = (WORD *) dc.out.p;
+		d.counters = (unsigned long long *) dc.counters.p; d.coeff = (double *) dc.coeff.p;
 		CU(cudaMemsetAsync(d.counters, 0, SSC_COUNTERS * sizeof(unsigned long long), d.stream));
-		CU(cudaMalloc(&d.coeff, (size_t) 3 * N * sizeof(double)));
 		if (job.op == OP_SUM) {
-			CU(cudaMalloc(&d.acc, (size_t) C * d.max_rows * W * sizeof(uint32_t)));
-			CU(cudaMalloc(&d.maxim, sizeof(unsigned long long)));
+			SSC_ENSURE(acc, (size_t) C * d.max_rows * W * sizeof(uint32_t));
+			SSC_ENSURE(maxim, sizeof(unsigned long long));
+			d.acc = (uint32_t *) dc.acc.p; d.maxim = (unsigned long long *) dc.maxim.p;
 			CU(cudaMemsetAsync(d.maxim, 0, sizeof(unsigned long long), d.stream));
 		}
 		if (need_norm) {
-			CU(cudaMalloc(&d.hist, (size_t) N * SSC_HIST_STRIDE * sizeof(uint32_t)));
+			SSC_ENSURE(hist, (size_t) N * SSC_HIST_STRIDE * sizeof(uint32_t));
+			d.hist = (uint32_t *) dc.hist.p;
 			CU(cudaMemsetAsync(d.hist, 0, (size_t) N * SSC_HIST_STRIDE * sizeof(uint32_t), d.stream));
 			if (g == 0) {
-				CU(cudaMalloc(&d.scratch, (size_t) N * 65536 * sizeof(uint32_t)));
-				CU(cudaMalloc(&d.stats, (size_t) 4 * N * sizeof(double)));
-				CU(cudaMalloc(&d.status, sizeof(int)));
+				SSC_ENSURE(scratch, (size_t) N * 65536 * sizeof(uint32_t));
+				SSC_ENSURE(stats, (size_t) 4 * N * sizeof(double));
+				SSC_ENSURE(status, sizeof(int));
+				d.scratch = (uint32_t *) dc.scratch.p; d.stats = (double *) dc.stats.p; d.status = (int *) dc.status.p;
 				CU(cudaMemsetAsync(d.status, 0, sizeof(int), d.stream));
 			}
 		}
@@ -415,11 +446,11 @@ int run_job(const Job &job) {
 				sh[f] = job.seq->sx[job.images[f]];
 				sh[N + f] = job.seq->sy[job.images[f]];
 			}
-			CU(cudaMalloc(&d.shifts, 2 * N * sizeof(int)));
+			SSC_ENSURE(shifts, 2 * N * sizeof(int));
+			d.shifts = (int *) dc.shifts.p;
 			CU(cudaMemcpyAsync(d.shifts, sh.data(), 2 * N * sizeof(int), cudaMemcpyHostToDevice, d.stream));
 			CU(cudaStreamSynchronize(d.stream));	// sh goes out of scope
 		}
-		CU(cudaEventRecord(d.ev[0], d.stream));
 	}
 
 	double t_h2d = 0, t_dev = 0, t_d2h = 0;
@@ -565,15 +596,44 @@ int run_job(const Job &job) {
 			}
 			if ((rc = phase_end(t_dev))) return rc;
 			if (job.op != OP_SUM || pass == 1) {
+				// device -> pinned bounce buffer (full PCIe speed), then into the malloc()ed result
+				if (g_pinned_cap < plane * C * sizeof(WORD)) {
+					if (g_pinned) cudaFreeHost(g_pinned);
+					g_pinned = nullptr; g_pinned_cap = 0;
+					if (cudaHostAlloc(&g_pinned, plane * C * sizeof(WORD), cudaHostAllocDefault) == cudaSuccess)
+						g_pinned_cap = plane * C * sizeof(WORD);
+				}
+				WORD *landing = g_pinned ? (WORD *) g_pinned : result;
 				for (int g = 0; g < G; g++) {
 					Dev &d = devs[g];
 					if (k >= d.pieces.size()) continue;
 					CU(cudaSetDevice(d.id));
 					const Piece &pc = d.pieces[k];
 					for (int c = 0; c < C; c++)
-						CU(cudaMemcpyAsync(result + (size_t) c * plane + (size_t) pc.row0 * W,
+						CU(cudaMemcpyAsync(landing + (size_t) c * plane + (size_t) pc.row0 * W,
 								d.out + (size_t) c * pc.rows * W, (size_t) pc.rows * W * sizeof(WORD),
 								cudaMemcpyDeviceToHost, d.stream));
+				}
+				for (auto &d : devs) {
+					CU(cudaSetDevice(d.id));
+					CU(cudaStreamSynchronize(d.stream));
+				}
+				if (landing != result) {
+					std::vector<std::thread> th;
+					for (int g = 0; g < G; g++) {
+						Dev &d = devs[g];
+						if (k >= d.pieces.size()) continue;
+						const Piece pc = d.pieces[k];
+						for (int c = 0; c < C; c++) {
+							const size_t off = (size_t) c * plane + (size_t) pc.row0 * W, cnt = (size_t) pc.rows * W;
+							const int parts = 4;
+							for (int q = 0; q < parts; q++) {
+								const size_t a = cnt * q / parts, z = cnt * (q + 1) / parts;
+								th.emplace_back([=] { memcpy(result + off + a, landing + off + a, (z - a) * sizeof(WORD)); });
+							}
+						}
+					}
+					for (auto &t : th) t.join();
 				}
 				if ((rc = phase_end(t_d2h))) return rc;
 			}
@@ -700,6 +760,19 @@ int finish(struct stacking_args *args, int rc, const char *what) {
 }  // namespace
 
 extern "C" {
+
+int ssc_release_workspace(void) {
+	std::lock_guard<std::mutex> op_lock(g_op_mu);
+	for (auto &kv : g_cache) {
+		cudaSetDevice(kv.first);
+		kv.second.release();
+	}
+	g_cache.clear();
+	if (g_pinned) cudaFreeHost(g_pinned);
+	g_pinned = nullptr;
+	g_pinned_cap = 0;
+	return SSC_OK;
+}
 
 int ssc_stack_summing(struct stacking_args *args) {
 	Job job;

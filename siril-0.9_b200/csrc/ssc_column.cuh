@@ -96,11 +96,11 @@ __device__ __forceinline__ int sigma_pass_sorted(Column c, int &o, int &N, doubl
 
 // stacking.c:1656-1794 for one column whose N samples are sorted ascending in
 // c[0..N) with S = sum, Q = sum of squares.  Returns the output sample.
-// unbias: optional table of (double) n / (double) (n - 1) for n <= 64 (the quotient itself is
-// the reference's; looking it up saves a division per iteration).
+// tables: optional small-n tables (ssc_device.cuh) that replace the divisions, bit for bit.
+template <bool SMALLN>
 static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int N, int rejection, double slow,
 		double shigh, unsigned long long S, unsigned long long Q, RejectState &st,
-		const double *unbias = nullptr) {
+		const SmallN *tables = nullptr) {
 	double sigma, median;
 	int n, r = 0, iter = 0, o = 0;
 
@@ -128,7 +128,7 @@ static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int
 	}
 	case SIGMA:		// stacking.c:1674-1695
 		do {
-			sigma = sd_from_sums(S, Q, N, unbias);
+			sigma = sd_from_sums<SMALLN>(S, Q, N, tables);
 			median = column_median(c, o, N);
 			n = sigma_pass_sorted(c, o, N, slow, shigh, sigma, median, r, S, Q, st);
 			if (++iter >= SSC_ITER_CAP) { st.cap = 1; break; }
@@ -136,7 +136,7 @@ static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int
 		break;
 	case SIGMEDIAN:		// stacking.c:1696-1709: rejected samples become round_to_WORD(median), N stays
 		do {
-			sigma = sd_from_sums(S, Q, N, unbias);
+			sigma = sd_from_sums<SMALLN>(S, Q, N, tables);
 			median = column_median(c, 0, N);
 			const unsigned int m = round_to_word(median);
 			const double tl = dmul(slow, sigma), th = dmul(shigh, sigma);
@@ -169,7 +169,7 @@ static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int
 		break;
 	case WINSORIZED:	// stacking.c:1710-1749
 		do {
-			sigma = sd_from_sums(S, Q, N, unbias);
+			sigma = sd_from_sums<SMALLN>(S, Q, N, tables);
 			median = column_median(c, o, N);
 			// w_stack is never materialised: clamping a sorted stack keeps it sorted and only
 			// ever rewrites a prefix (to one value) and a suffix (to one value), so
@@ -209,7 +209,7 @@ static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int
 				const unsigned long long Sw = Sm + (unsigned long long) clo * vlo + (unsigned long long) chi * vhi;
 				const unsigned long long Qw = Qm + (unsigned long long) clo * sq(vlo) + (unsigned long long) chi * sq(vhi);
 				sigma0 = sigma;
-				sigma = dmul(1.134, sd_from_sums(Sw, Qw, N, unbias));
+				sigma = dmul(1.134, sd_from_sums<SMALLN>(Sw, Qw, N, tables));
 				if (++inner >= SSC_ITER_CAP) { st.cap = 1; break; }
 			} while (ddiv(fabs(dsub(sigma, sigma0)), sigma0) > 0.0005);
 			n = sigma_pass_sorted(c, o, N, slow, shigh, sigma, median, r, S, Q, st);
@@ -264,7 +264,7 @@ static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int
 		break;
 	}
 	// stacking.c:1790-1794: the double sum of WORDs is exact, S is that sum
-	return round_to_word(ddiv((double) (long long) S, (double) N));
+	return mean_to_word<SMALLN>(S, N, tables);
 }
 
 }  // namespace ssc

@@ -47,12 +47,49 @@ __device__ __forceinline__ unsigned int normalize_sample(unsigned int p, int mod
 // variance carries a single rounding; then the reference's own
 // sqrt(variance * (n / (n-1))).  GSL accumulates the same quantity in x87
 // long double, which FP64 cannot reproduce bit for bit.
+// Small-n tables (n <= 64) that take the divisions out of the per-pixel loops without changing a
+// bit: unbias[n] = n / (n-1) is the reference's own quotient; inv_n[n] = RN(1/n) and
+// inv_n2[n] = RN(1/n^2) feed div_exact() below.
+struct SmallN {
+	const double *unbias, *inv_n, *inv_n2;
+};
+#define SSC_SMALLN_MAX 64
+
+// a / b correctly rounded, given y = RN(1 / b): q0 = RN(a*y), r = a - b*q0 (exact in one FMA),
+// q = RN(q0 + r*y).  Markstein's theorem: this is RN(a / b) whenever y is the correctly rounded
+// reciprocal and b's significand is not all ones -- b is a small integer here.  The explicit FMAs
+// are part of the division algorithm (as inside __ddiv_rn itself), not contractions of the
+// reference's arithmetic.
+__device__ __forceinline__ double div_exact(double a, double b, double y) {
+	const double q0 = dmul(a, y);
+	const double r = __fma_rn(-b, q0, a);
+	return __fma_rn(r, y, q0);
+}
+
+// SMALLN: the caller guarantees n <= SSC_SMALLN_MAX and passes the tables (no fallback code then)
+template <bool SMALLN>
 __device__ __forceinline__ double sd_from_sums(unsigned long long S, unsigned long long Q, int n,
-		const double *unbias = nullptr) {
-	unsigned long long D = (unsigned long long) n * Q - S * S;
-	double var = ddiv(__ull2double_rn(D), (double) ((long long) n * n));
-	double nn1 = (unbias && n <= 64) ? unbias[n] : ddiv((double) n, (double) (n - 1));
+		const SmallN *t = nullptr) {
+	const unsigned long long D = (unsigned long long) n * Q - S * S;
+	double var, nn1;
+	if constexpr (SMALLN) {
+		// D < n^2 * 2^32 <= 2^44: exact through the 2^52 mantissa trick, no conversion unit
+		const double d = dsub(__hiloint2double(0x43300000 | (int) (D >> 32), (int) (unsigned int) D), 4503599627370496.0);
+		var = div_exact(d, (double) (n * n), t->inv_n2[n]);
+		nn1 = t->unbias[n];
+	} else {
+		var = ddiv(__ull2double_rn(D), (double) ((long long) n * n));
+		nn1 = ddiv((double) n, (double) (n - 1));
+	}
 	return dsqrt(dmul(var, nn1));
+}
+
+// stacking.c:1794: round_to_WORD(sum / (double) N), the sum being an exact integer
+template <bool SMALLN>
+__device__ __forceinline__ unsigned int mean_to_word(unsigned long long S, int n, const SmallN *t = nullptr) {
+	const double s = (double) (long long) S;
+	if constexpr (SMALLN) return round_to_word(div_exact(s, (double) n, t->inv_n[n]));
+	else return round_to_word(ddiv(s, (double) n));
 }
 
 // sigma_clipping, stacking.c:1148-1161: -1 low, +1 high, 0 keep

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(FAST_THREADS, SSC_FAST_RESIDENT_THREADS / FAST
 k_stack_fast(StackParams p, int is_median) {
 	extern __shared__ unsigned int cols[];		// [NP][FAST_THREADS] packed columns
 	__shared__ double s_coef[3 * 64];
-	__shared__ double s_unbias[65];			// (double) n / (double) (n - 1), the reference's own quotient
+	__shared__ double s_unbias[65], s_inv_n[65], s_inv_n2[65];	// small-n tables (ssc_device.cuh)
 	__shared__ int s_fast_norm;
 	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
 	__shared__ unsigned int s_qcount;			// work queue of pixels whose first pass rejects something
@@ -120,7 +120,12 @@ k_stack_fast(StackParams p, int is_median) {
 
 	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
 	if (tid == 0) s_fast_norm = 1;
-	if (tid >= 2 && tid <= 64) s_unbias[tid] = ddiv((double) tid, (double) (tid - 1));
+	if (tid >= 1 && tid <= 64) {
+		s_unbias[tid] = tid > 1 ? ddiv((double) tid, (double) (tid - 1)) : 0.0;
+		s_inv_n[tid] = ddiv(1.0, (double) tid);
+		s_inv_n2[tid] = ddiv(1.0, (double) (tid * tid));
+	}
+	const SmallN tables{s_unbias, s_inv_n, s_inv_n2};
 	__syncthreads();
 	if (norm && tid < N) {
 		const double off = p.coeff[tid], mul = p.coeff[N + tid], sc = p.coeff[2 * N + tid];
@@ -226,8 +231,8 @@ k_stack_fast(StackParams p, int is_median) {
 		const unsigned long long S[2] = {Sa, Sb}, Q[2] = {Qa, Qb};
 		if (p.rejection == NO_REJEC) {
 			// stacking.c:1790-1794 with nothing rejected: no ordering needed at all
-			res[0] = round_to_word(ddiv((double) (long long) S[0], (double) N));
-			res[1] = round_to_word(ddiv((double) (long long) S[1], (double) N));
+			res[0] = mean_to_word<true>(S[0], N, &tables);
+			res[1] = mean_to_word<true>(S[1], N, &tables);
 		} else {
 			sort_network<NP>(v);
 #pragma unroll
@@ -259,13 +264,13 @@ k_stack_fast(StackParams p, int is_median) {
 						flagged = clip_percentile(lo, p.sig_low, p.sig_high, median) != 0
 								|| clip_percentile(hi, p.sig_low, p.sig_high, median) != 0;
 					} else {
-						const double sigma = sd_from_sums(S[h], Q[h], N, s_unbias);
+						const double sigma = sd_from_sums<true>(S[h], Q[h], N, &tables);
 						flagged = clip_sigma(lo, p.sig_low, p.sig_high, sigma, median) != 0
 								|| clip_sigma(hi, p.sig_low, p.sig_high, sigma, median) != 0;
 					}
 				}
 				pending[h] = flagged && active;	// padding threads of the last block own no pixel
-				res[h] = round_to_word(ddiv((double) (long long) S[h], (double) N));
+				res[h] = mean_to_word<true>(S[h], N, &tables);
 			}
 			if (tid == 0) s_qcount = 0;
 			s_layer[tid] = (unsigned char) layer;
@@ -290,8 +295,8 @@ k_stack_fast(StackParams p, int is_median) {
 				const unsigned int item = s_qitem[i];
 				Column c{cols16 + item, 2 * FAST_THREADS};
 				RejectState ist{0, 0, 0, 0};
-				const unsigned int r = reject_sorted_and_mean(c, N, p.rejection, p.sig_low, p.sig_high,
-						s_S[item], s_Q[item], ist, s_unbias);
+				const unsigned int r = reject_sorted_and_mean<true>(c, N, p.rejection, p.sig_low, p.sig_high,
+						s_S[item], s_Q[item], ist, &tables);
 				s_res[item] = (unsigned short) r;
 				const int il = s_layer[item >> 1];
 				if (ist.rej_lo) atomicAdd(&blk_counters[il * 2 + 0], (unsigned long long) ist.rej_lo);

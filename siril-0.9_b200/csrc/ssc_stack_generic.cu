@@ -98,7 +98,7 @@ __global__ void k_stack_generic(StackParams p, PixelSource src, int n_pad, int i
 			int lhs = (N - 1) >> 1, rhs = N >> 1;
 			result = (c.get(lhs) + c.get(rhs)) >> 1;
 		} else {
-			result = reject_sorted_and_mean(c, N, p.rejection, p.sig_low, p.sig_high, S, Q, st);
+			result = reject_sorted_and_mean<false>(c, N, p.rejection, p.sig_low, p.sig_high, S, Q, st);
 		}
 		p.out[(size_t) layer * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W + x] = (WORD) result;
 
