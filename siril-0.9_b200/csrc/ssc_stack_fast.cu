@@ -95,13 +95,29 @@ __device__ __forceinline__ void normalize_all(unsigned int (&v)[NP], int N, cons
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// Leftover list: pixels the register-resident rejection could not finish (more rejections than
+// its window holds, or more passes than it unrolls) are appended -- sorted column, result
+// address, layer -- to a device-global list and finished by k_stack_leftover, one pixel per
+// thread with full warps.  A typical deep-sky stack parks well under 1 % of its pixels here.
+// ---------------------------------------------------------------------------------------------
+struct LeftoverList {
+	unsigned int *count;		// items appended (may exceed capacity: the excess was handled in place)
+	unsigned int capacity;
+	uint4 *cols;			// [capacity][NP * 2 bytes]: the sorted column of each item, contiguous
+	uint2 *meta;			// [capacity]: result element index, layer
+};
+
+enum { MODE_MEDIAN = 0, MODE_NOREJ = 1, MODE_SIGMA_REG = 2, MODE_QUEUE = 3 };
+
 // FULL: n_frames == NP (no sentinel padding, no per-frame bound checks in the unrolled code)
-#ifndef SSC_FAST_RESIDENT_THREADS
-#define SSC_FAST_RESIDENT_THREADS 512	// threads per SM the register budget is sized for
-#endif
-template <int NP, bool FULL, int FAST_THREADS>
-__global__ void __launch_bounds__(FAST_THREADS, SSC_FAST_RESIDENT_THREADS / FAST_THREADS)
-k_stack_fast(StackParams p, int is_median) {
+// MODE: which tail follows the network (one per instantiation: the kernel is instruction-fetch
+//       sensitive, dead alternatives are not carried along)
+constexpr int FAST_THREADS = 128;
+
+template <int NP, bool FULL, int MODE>
+__global__ void __launch_bounds__(FAST_THREADS, 4)
+k_stack_fast(StackParams p, LeftoverList list) {
 	extern __shared__ unsigned int cols[];		// [NP][FAST_THREADS] packed columns
 	__shared__ double s_coef[3 * 64];
 	__shared__ double s_unbias[65], s_inv_n[65], s_inv_n2[65];	// small-n tables (ssc_device.cuh)
@@ -151,6 +167,7 @@ k_stack_fast(StackParams p, int is_median) {
 	// per-thread offset inside a frame (32 bits: a frame holds < 2^32 pixel pairs) on top of a
 	// block-uniform per-frame base, so the 64 address computations stay off the ALU pipe
 	const unsigned int toff = (unsigned int) ((((size_t) layer * b.layer_stride + (size_t) (srow - b.buf_row0) * W) >> 1) + x2);
+	const unsigned int out_idx = (unsigned int) ((size_t) layer * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W + 2 * x2);
 	const unsigned int *frames32 = reinterpret_cast<const unsigned int *>(b.frames);
 	const size_t fstride2 = b.frame_stride >> 1;
 
@@ -193,20 +210,24 @@ k_stack_fast(StackParams p, int is_median) {
 	}
 
 	unsigned int res[2];
-	if (is_median) {
+	WORD *dst = p.out + out_idx;
+
+	if constexpr (MODE == MODE_MEDIAN) {
 		sort_network<NP>(v);			// sentinels (0xFFFF) sort behind the N samples
+		unsigned int lo, hi;
 		if (FULL) {				// stacking.c:765-767: truncating median, straight from registers
-			const unsigned int lo = v[NP / 2 - 1], hi = v[NP / 2];
-			res[0] = ((lo & 0xFFFFu) + (hi & 0xFFFFu)) >> 1;
-			res[1] = ((lo >> 16) + (hi >> 16)) >> 1;
+			lo = v[NP / 2 - 1];
+			hi = v[NP / 2];
 		} else {
 #pragma unroll
 			for (int f = 0; f < NP; f++) cols[f * FAST_THREADS + tid] = v[f];
-			const int lhs = (N - 1) >> 1, rhs = N >> 1;
-			const unsigned int lo = cols[lhs * FAST_THREADS + tid], hi = cols[rhs * FAST_THREADS + tid];
-			res[0] = ((lo & 0xFFFFu) + (hi & 0xFFFFu)) >> 1;
-			res[1] = ((lo >> 16) + (hi >> 16)) >> 1;
+			lo = cols[((N - 1) >> 1) * FAST_THREADS + tid];
+			hi = cols[(N >> 1) * FAST_THREADS + tid];
 		}
+		res[0] = ((lo & 0xFFFFu) + (hi & 0xFFFFu)) >> 1;
+		res[1] = ((lo >> 16) + (hi >> 16)) >> 1;
+		if (active) *reinterpret_cast<unsigned int *>(dst) = res[0] | (res[1] << 16);
+		return;
 	} else {
 		// exact integer sums of the (normalized) samples; the sum fits 32 bits and comes straight
 		// from the packed words (IDP.2A: acc + lo16 * 1 + hi16 * 0), the sum of squares needs 64
@@ -218,7 +239,7 @@ k_stack_fast(StackParams p, int is_median) {
 				Sb = __dp2a_lo(v[f], 0x0100u, Sb);
 			}
 		}
-		if (!have_q) {
+		if (!have_q && MODE != MODE_NOREJ) {
 #pragma unroll
 			for (int f = 0; f < NP; f++) {
 				if (FULL || f < N) {
@@ -228,12 +249,135 @@ k_stack_fast(StackParams p, int is_median) {
 				}
 			}
 		}
-		const unsigned long long S[2] = {Sa, Sb}, Q[2] = {Qa, Qb};
-		if (p.rejection == NO_REJEC) {
+		unsigned long long S[2] = {Sa, Sb}, Q[2] = {Qa, Qb};
+
+		if constexpr (MODE == MODE_NOREJ) {
 			// stacking.c:1790-1794 with nothing rejected: no ordering needed at all
 			res[0] = mean_to_word<true>(S[0], N, &tables);
 			res[1] = mean_to_word<true>(S[1], N, &tables);
-		} else {
+			if (active) *reinterpret_cast<unsigned int *>(dst) = res[0] | (res[1] << 16);
+			return;
+		} else if constexpr (MODE == MODE_SIGMA_REG) {
+			// ---- sigma clipping (stacking.c:1674-1695) entirely in registers.  In a sorted stack the
+			// low flags are a prefix and the high flags a suffix, the survivors stay [nl, NP - nh), and
+			// each pass only looks at the sums, the two middle survivors and the next candidates at
+			// both ends -- all of which sit at STATIC register indices as long as few samples go:
+			// candidates v[0..2] below, v[NP-1..NP-6] above, medians within v[NP/2-3..NP/2+1].  Both
+			// pixels of the pair run side by side.  Whoever needs more (a third low, a sixth high, a
+			// fifth pass) is handed to the leftover list.  With NP >= 32 and at most 7 rejections the
+			// reference's "N - r <= 4" break (:1684) cannot be reached here.
+			static_assert(FULL && NP >= 32, "register-resident clipping needs a full stack of >= 32 frames");
+			sort_network<NP>(v);
+			int nl[2] = {0, 0}, nh[2] = {0, 0};
+			unsigned int rl[2] = {0, 0}, rh[2] = {0, 0};
+			bool done[2] = {false, false}, punt[2] = {false, false};
+#pragma unroll 1
+			for (int it = 0; it < 5; it++) {
+				if (it == 4) {			// a fifth pass would be needed
+					punt[0] = !done[0];
+					punt[1] = !done[1];
+					break;
+				}
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					if (done[h] || punt[h]) continue;
+					const int Nc = NP - nl[h] - nh[h];
+					const double sigma = sd_from_sums<true>(S[h], Q[h], Nc, &tables);
+					const int lhs = nl[h] + ((Nc - 1) >> 1), rhs = nl[h] + (Nc >> 1);
+					unsigned int ml = 0, mr = 0;
+#pragma unroll
+					for (int k = NP / 2 - 3; k <= NP / 2 + 1; k++) {
+						const unsigned int e = h ? v[k] >> 16 : v[k] & 0xFFFFu;
+						if (lhs == k) ml = e;
+						if (rhs == k) mr = e;
+					}
+					const double median = lhs == rhs ? (double) (int) ml : dmul((double) (int) (ml + mr), 0.5);
+					const double tl = dmul(p.sig_low, sigma), th = dmul(p.sig_high, sigma);
+					int n = 0;
+#pragma unroll
+					for (int k = 0; k < 3; k++) {		// low candidates, in scan order (sigma_clipping, :1152)
+						const unsigned int e = h ? v[k] >> 16 : v[k] & 0xFFFFu;
+						if (nl[h] == k && dsub(median, (double) (int) e) > tl) {
+							nl[h]++; n++; rl[h]++;
+							S[h] -= e; Q[h] -= (unsigned long long) e * e;
+						}
+					}
+#pragma unroll
+					for (int k = 0; k < 6; k++) {		// high candidates, from the top (:1156)
+						const unsigned int e = h ? v[NP - 1 - k] >> 16 : v[NP - 1 - k] & 0xFFFFu;
+						if (nh[h] == k && dsub((double) (int) e, median) > th) {
+							nh[h]++; n++; rh[h]++;
+							S[h] -= e; Q[h] -= (unsigned long long) e * e;
+						}
+					}
+					if (nl[h] == 3 || nh[h] == 6) punt[h] = true;	// the next candidate is out of the window
+					else if (n == 0) done[h] = true;		// do { } while (n > 0 && N > 3)
+				}
+				if ((done[0] || punt[0]) && (done[1] || punt[1])) break;
+			}
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				res[h] = mean_to_word<true>(S[h], NP - nl[h] - nh[h], &tables);
+				punt[h] = punt[h] && active;
+			}
+			// ---- finished pixels: results and counters ----
+			if (active) {
+				if (!punt[0] && !punt[1]) {
+					*reinterpret_cast<unsigned int *>(dst) = res[0] | (res[1] << 16);
+				} else {
+					if (!punt[0]) dst[0] = (WORD) res[0];
+					if (!punt[1]) dst[1] = (WORD) res[1];
+				}
+				const unsigned int cl = (punt[0] ? 0 : rl[0]) + (punt[1] ? 0 : rl[1]);
+				const unsigned int ch = (punt[0] ? 0 : rh[0]) + (punt[1] ? 0 : rh[1]);
+				if (cl) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) cl);
+				if (ch) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) ch);
+			}
+			// ---- the others: to the leftover list (one atomic per warp), or in place if it is full ----
+			bool in_place = false;
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				const unsigned int mask = __ballot_sync(0xffffffffu, punt[h]);
+				if (mask == 0) continue;
+				const int lane = tid & 31;
+				unsigned int base = 0;
+				if (lane == __ffs(mask) - 1) base = atomicAdd(list.count, (unsigned int) __popc(mask));
+				base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+				if (punt[h]) {
+					const unsigned int slot = base + __popc(mask & ((1u << lane) - 1));
+					if (slot < list.capacity) {
+						uint4 *d = list.cols + (size_t) slot * (NP / 8);
+#pragma unroll
+						for (int q = 0; q < NP / 8; q++) {
+							const unsigned int sel = h ? 0x7632u : 0x5410u;
+							d[q] = make_uint4(__byte_perm(v[8 * q], v[8 * q + 1], sel), __byte_perm(v[8 * q + 2], v[8 * q + 3], sel),
+									__byte_perm(v[8 * q + 4], v[8 * q + 5], sel), __byte_perm(v[8 * q + 6], v[8 * q + 7], sel));
+						}
+						list.meta[slot] = make_uint2(out_idx + h, (unsigned int) layer);
+						punt[h] = false;
+					} else {
+						in_place = true;
+					}
+				}
+			}
+			if (__syncthreads_or(in_place)) {	// list full (adversarial data): finish in place, slowly
+#pragma unroll
+				for (int f = 0; f < NP; f++) cols[f * FAST_THREADS + tid] = v[f];
+#pragma unroll 1
+				for (int h = 0; h < 2; h++) {
+					if (!punt[h]) continue;
+					Column c{reinterpret_cast<WORD *>(cols) + 2 * tid + h, 2 * FAST_THREADS};
+					unsigned long long s0 = 0, q0 = 0;
+					for (int f = 0; f < NP; f++) { const unsigned int e = c.get(f); s0 += e; q0 += sq(e); }
+					RejectState ist{0, 0, 0, 0};
+					dst[h] = (WORD) reject_sorted_and_mean<true>(c, NP, SIGMA, p.sig_low, p.sig_high, s0, q0, ist, &tables);
+					if (ist.rej_lo) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) ist.rej_lo);
+					if (ist.rej_hi) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) ist.rej_hi);
+					if (ist.guard) atomicAdd(&blk_counters[6], 1ull);
+					if (ist.cap) atomicAdd(&blk_counters[7], 1ull);
+				}
+			}
+		} else {	// MODE_QUEUE: every other rejection / stack size, through the block's work queue
 			sort_network<NP>(v);
 #pragma unroll
 			for (int f = 0; f < NP; f++)
@@ -243,8 +387,7 @@ k_stack_fast(StackParams p, int is_median) {
 			// ---- phase 1: can the first pass flag anything at all?  Flags are monotone in the
 			// sample value (low flags a prefix, high flags a suffix of the sorted stack), so when
 			// neither the smallest nor the largest sample is flagged nothing is, the reference's
-			// do-while ends after one pass (n == 0) and the result is the plain mean.  Both pixels
-			// are evaluated side by side from registers; only the others go to the work queue.
+			// do-while ends after one pass (n == 0) and the result is the plain mean.
 			// (with N <= 4 the reference's "N - r <= 4" break is taken at the very first sample:
 			// that pixel must go through the full pass so that the event is counted)
 			const bool quick = (p.rejection == SIGMA && N > 4) || p.rejection == SIGMEDIAN || p.rejection == PERCENTILE;
@@ -286,12 +429,10 @@ k_stack_fast(StackParams p, int is_median) {
 			}
 			__syncthreads();
 
-			// ---- phase 2: the pending pixels, spread over all warps of the block (their sorted
+			// ---- phase 2: the pending pixels, densely packed over the block's threads (their sorted
 			// columns sit in shared memory, any thread can run them) ----
 			const unsigned int n_items = s_qcount;
-			constexpr int NWARPS = FAST_THREADS / 32;
-			(void) NWARPS;
-			for (unsigned int i = tid; i < n_items; i += FAST_THREADS) {	// dense: full warps run the heavy code
+			for (unsigned int i = tid; i < n_items; i += FAST_THREADS) {
 				const unsigned int item = s_qitem[i];
 				Column c{cols16 + item, 2 * FAST_THREADS};
 				RejectState ist{0, 0, 0, 0};
@@ -307,13 +448,60 @@ k_stack_fast(StackParams p, int is_median) {
 			__syncthreads();
 			if (pending[0]) res[0] = s_res[2 * tid];
 			if (pending[1]) res[1] = s_res[2 * tid + 1];
+			if (active) *reinterpret_cast<unsigned int *>(dst) = res[0] | (res[1] << 16);
 		}
 	}
+	__syncthreads();
+	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
+		atomicAdd(&p.counters[tid], blk_counters[tid]);
+}
 
-	if (active) {
-		unsigned int *dst = reinterpret_cast<unsigned int *>(
-				p.out + (size_t) layer * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W) + x2;
-		*dst = res[0] | (res[1] << 16);
+// The leftover list, one pixel per thread: the column is already sorted, the sums are rebuilt.
+template <int NP>
+__global__ void __launch_bounds__(128)
+k_stack_leftover(StackParams p, LeftoverList list) {
+	__shared__ WORD col[NP * 128];
+	__shared__ double s_unbias[65], s_inv_n[65], s_inv_n2[65];
+	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
+	const int tid = threadIdx.x;
+	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
+	if (tid >= 1 && tid <= 64) {
+		s_unbias[tid] = tid > 1 ? ddiv((double) tid, (double) (tid - 1)) : 0.0;
+		s_inv_n[tid] = ddiv(1.0, (double) tid);
+		s_inv_n2[tid] = ddiv(1.0, (double) (tid * tid));
+	}
+	const SmallN tables{s_unbias, s_inv_n, s_inv_n2};
+	__syncthreads();
+	unsigned int n_items = *list.count;
+	if (n_items > list.capacity) n_items = list.capacity;
+	for (unsigned int base = blockIdx.x * 128; base < n_items; base += gridDim.x * 128) {
+		const unsigned int i = base + tid;
+		if (i < n_items) {
+			Column c{col + tid, 128};
+			const uint4 *src = list.cols + (size_t) i * (NP / 8);
+			unsigned long long S = 0, Q = 0;
+#pragma unroll
+			for (int q = 0; q < NP / 8; q++) {
+				const uint4 w = src[q];
+				const unsigned int ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const unsigned int a = ww[k] & 0xFFFFu, bq = ww[k] >> 16;
+					c.set(8 * q + 2 * k, a);
+					c.set(8 * q + 2 * k + 1, bq);
+					S += a + bq;
+					Q += sq(a) + sq(bq);
+				}
+			}
+			RejectState ist{0, 0, 0, 0};
+			const unsigned int r = reject_sorted_and_mean<true>(c, NP, p.rejection, p.sig_low, p.sig_high, S, Q, ist, &tables);
+			const uint2 m = list.meta[i];
+			p.out[m.x] = (WORD) r;
+			if (ist.rej_lo) atomicAdd(&blk_counters[m.y * 2 + 0], (unsigned long long) ist.rej_lo);
+			if (ist.rej_hi) atomicAdd(&blk_counters[m.y * 2 + 1], (unsigned long long) ist.rej_hi);
+			if (ist.guard) atomicAdd(&blk_counters[6], 1ull);
+			if (ist.cap) atomicAdd(&blk_counters[7], 1ull);
+		}
 	}
 	__syncthreads();
 	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
@@ -328,42 +516,86 @@ bool fast_path_eligible(const StackParams &p, int is_median) {
 	if (!is_median && (b.shiftx || b.shifty)) return false;
 	if ((b.width & 1) || (b.frame_stride & 1) || (b.layer_stride & 1)) return false;
 	if (((uintptr_t) b.frames & 3) || ((uintptr_t) p.out & 3) || (p.out_layer_stride & 1)) return false;
+	if ((size_t) b.layers * p.out_layer_stride >= 0xFFFFFFF0ull) return false;	// 32-bit result indices
 	return true;
 }
 
-// Threads per block: more warps of one block per scheduler run the same straight-line code
-// close together and share instruction fetches (SSC_FAST_TPB overrides, for experiments).
-static int fast_threads() {
-	static int tpb = 0;
-	if (!tpb) {
-		const char *e = getenv("SSC_FAST_TPB");
-		tpb = e ? atoi(e) : 256;
-		if (tpb != 128 && tpb != 256 && tpb != 512) tpb = 256;
+// Leftover-list storage, kept per device between launches (grown on demand; the first launch of
+// a larger shape allocates, i.e. synchronises once).
+struct LeftoverStore {
+	unsigned int *count = nullptr;
+	void *cols = nullptr;
+	void *meta = nullptr;
+	size_t capacity = 0, col_bytes = 0;
+};
+static LeftoverStore g_leftover[64];
+
+static int leftover_list(int np, unsigned long long pixels, LeftoverList &list, cudaStream_t stream) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) return SSC_ERR_ARG;
+	LeftoverStore &st = g_leftover[dev];
+	size_t want = (size_t) (pixels / 16) + 65536;	// 6 % of the pixels; beyond that pixels finish in place
+	if (want > 0x7FFFFFF0ull) want = 0x7FFFFFF0ull;
+	if (!st.count && cudaMalloc(&st.count, sizeof(unsigned int)) != cudaSuccess) return SSC_ERR_CUDA;
+	if (st.capacity < want || st.col_bytes < (size_t) np * 2) {
+		if (st.cols) cudaFree(st.cols);
+		if (st.meta) cudaFree(st.meta);
+		st.cols = st.meta = nullptr;
+		st.capacity = 0;
+		if (cudaMalloc(&st.cols, want * 128) != cudaSuccess) return SSC_ERR_CUDA;	// room for 64-frame columns
+		if (cudaMalloc(&st.meta, want * sizeof(uint2)) != cudaSuccess) return SSC_ERR_CUDA;
+		st.capacity = want;
+		st.col_bytes = 128;
 	}
-	return tpb;
+	if (cudaMemsetAsync(st.count, 0, sizeof(unsigned int), stream) != cudaSuccess) return SSC_ERR_CUDA;
+	list.count = st.count;
+	list.capacity = (unsigned int) st.capacity;
+	list.cols = (uint4 *) st.cols;
+	list.meta = (uint2 *) st.meta;
+	return SSC_OK;
 }
 
-template <int NP, bool FULL, int TPB>
-static int launch_fast_cfg(const StackParams &p, int is_median, cudaStream_t stream) {
+template <int NP, bool FULL, int MODE>
+static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 	const ssc_band &b = p.band;
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * (b.width >> 1);
 	if (total == 0) return SSC_OK;
-	const size_t smem = (size_t) NP * TPB * sizeof(unsigned int);
-	if (cudaFuncSetAttribute(k_stack_fast<NP, FULL, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
+	const size_t smem = (size_t) NP * FAST_THREADS * sizeof(unsigned int);
+	if (cudaFuncSetAttribute(k_stack_fast<NP, FULL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
-	const unsigned int grid = (unsigned int) ((total + TPB - 1) / TPB);
-	k_stack_fast<NP, FULL, TPB><<<grid, TPB, smem, stream>>>(p, is_median);
-	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
+	const unsigned long long blocks = (total + FAST_THREADS - 1) / FAST_THREADS;
+	if (blocks > 0x7FFFFFFFull) return SSC_ERR_ARG;
+	LeftoverList list{nullptr, 0, nullptr, nullptr};
+	if (MODE == MODE_SIGMA_REG) {
+		int rc = leftover_list(NP, total * 2, list, stream);
+		if (rc) return rc;
+	}
+	k_stack_fast<NP, FULL, MODE><<<(unsigned int) blocks, FAST_THREADS, smem, stream>>>(p, list);
+	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
+	if constexpr (MODE == MODE_SIGMA_REG) {
+		int dev = 0, sms = 148;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		k_stack_leftover<NP><<<sms * 8, 128, 0, stream>>>(p, list);
+		if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
+	}
+	return SSC_OK;
 }
 
 template <int NP>
 static int launch_fast_np(const StackParams &p, int is_median, cudaStream_t stream) {
 	const bool full = p.band.n_frames == NP;
-	switch (fast_threads()) {
-	case 128: return full ? launch_fast_cfg<NP, true, 128>(p, is_median, stream) : launch_fast_cfg<NP, false, 128>(p, is_median, stream);
-	case 512: return full ? launch_fast_cfg<NP, true, 512>(p, is_median, stream) : launch_fast_cfg<NP, false, 512>(p, is_median, stream);
-	default: return full ? launch_fast_cfg<NP, true, 256>(p, is_median, stream) : launch_fast_cfg<NP, false, 256>(p, is_median, stream);
+	if (is_median)
+		return full ? launch_fast_cfg<NP, true, MODE_MEDIAN>(p, stream) : launch_fast_cfg<NP, false, MODE_MEDIAN>(p, stream);
+	if (p.rejection == NO_REJEC)
+		return full ? launch_fast_cfg<NP, true, MODE_NOREJ>(p, stream) : launch_fast_cfg<NP, false, MODE_NOREJ>(p, stream);
+	if constexpr (NP >= 32) {
+		// (non-negative parameters: a sample above the median is then never "low", one below never "high")
+		if (full && p.rejection == SIGMA && p.sig_low >= 0.0 && p.sig_high >= 0.0)
+			return launch_fast_cfg<NP, true, MODE_SIGMA_REG>(p, stream);
 	}
+	return full ? launch_fast_cfg<NP, true, MODE_QUEUE>(p, stream) : launch_fast_cfg<NP, false, MODE_QUEUE>(p, stream);
 }
 
 int launch_stack_fast(const StackParams &p, int is_median, cudaStream_t stream) {
