@@ -27,9 +27,12 @@ int launch_stack_generic(const StackParams &p, const unsigned int *list, const u
 // ssc_stack_fast.cu
 bool fast_path_eligible(const StackParams &p, int is_median);
 int launch_stack_fast(const StackParams &p, int is_median, cudaStream_t stream);
+// ssc_stack_pipe.cu
+bool pipe_path_eligible(const StackParams &p, int is_median);
+int launch_stack_pipe(const StackParams &p, cudaStream_t stream);
 // picks the register-network kernel when the shape allows it, the general kernel otherwise
 int launch_stack(const StackParams &p, int is_median, cudaStream_t stream);
-extern int g_kernel_path;	// 0 automatic, 1 general kernel only (ssc_set_kernel_path)
+extern int g_kernel_path;	// 0 automatic, 1 general kernel only, 2 warp-specialised pipeline where eligible (ssc_set_kernel_path)
 
 // ssc_sum.cu
 int launch_sum_accumulate(const ssc_band &b, uint32_t *acc, unsigned long long *maxim, cudaStream_t stream);

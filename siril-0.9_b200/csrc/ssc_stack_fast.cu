@@ -22,63 +22,11 @@
 #include <cstdlib>
 #include "ssc_column.cuh"
 #include "ssc_kernels.h"
-#include "ssc_sortnet.h"
+#include "ssc_network.cuh"
+#include "ssc_leftover.cuh"
 
 namespace ssc {
 
-
-__device__ __forceinline__ double word_to_double(unsigned int p) {
-	return dsub(__hiloint2double(0x43300000, (int) p), 4503599627370496.0);	// (2^52 + p) - 2^52, exact
-}
-
-// round_to_WORD (utils.c:68-74) for |y| < 2^31: floor(y + 0.5) read from the low word of
-// (y + 0.5) +rz 1.5*2^52, then max(min(., 65535), 0).  Equals the reference for every such y:
-// y <= 0 -> floor <= 0 -> 0;  0 < y <= 65535 -> trunc(y + 0.5);  y > 65535 -> >= 65535 -> 65535.
-#ifndef SSC_NORM_XU_OUT
-#define SSC_NORM_XU_OUT 0
-#endif
-__device__ __forceinline__ unsigned int round_to_word_fast(double y) {
-#if SSC_NORM_XU_OUT
-	// F2I.F64.TRUNC saturates and maps NaN to 0: valid for every y, costs a conversion-unit slot
-	return (unsigned int) __vimin_s32_relu(__double2int_rz(dadd(y, 0.5)), 65535);
-#else
-	double u = __dadd_rz(dadd(y, 0.5), 6755399441055744.0);
-	return (unsigned int) __vimin_s32_relu(__double2loint(u), 65535);
-#endif
-}
-
-template <int NP>
-__device__ __forceinline__ void sort_network(unsigned int (&v)[NP]) {
-#define SSC_CE(a, b) { unsigned int lo_ = __vminu2(v[a], v[b]); v[b] = __vmaxu2(v[a], v[b]); v[a] = lo_; }
-	if constexpr (NP == 16) { SSC_SORTNET_16 }
-	else if constexpr (NP == 32) { SSC_SORTNET_32 }
-	else { SSC_SORTNET_64 }
-#undef SSC_CE
-}
-
-// One sample pair through normalization (stacking.c:1635-1652), KIND = the reference's enum value.
-// ADDITIVE / MULTIPLICATIVE have scale == 1.0 exactly (stacking.c:130-134), and x * 1.0 == x.
-template <int KIND>
-__device__ __forceinline__ unsigned int normalize_pair_fast(unsigned int w, double off, double mul, double sc,
-		unsigned long long &Qa, unsigned long long &Qb) {
-	// I2F.F64.U16 reads either half of the packed word directly (conversion unit, off the ALU pipe)
-	double da = (double) (unsigned short) (w & 0xFFFFu), db = (double) (unsigned short) (w >> 16);
-	if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) {
-		da = dmul(da, sc);
-		db = dmul(db, sc);
-	}
-	if constexpr (KIND == ADDITIVE || KIND == ADDITIVE_SCALING) {
-		da = dsub(da, off);
-		db = dsub(db, off);
-	} else {
-		da = dmul(da, mul);
-		db = dmul(db, mul);
-	}
-	const unsigned int ra = round_to_word_fast(da), rb = round_to_word_fast(db);
-	Qa += (unsigned long long) ra * ra;	// IMAD.WIDE on the values while they are still unpacked
-	Qb += (unsigned long long) rb * rb;
-	return ra | (rb << 16);
-}
 
 template <int NP, bool FULL, int KIND>
 __device__ __forceinline__ void normalize_all(unsigned int (&v)[NP], int N, const double *s_coef,
@@ -95,19 +43,9 @@ __device__ __forceinline__ void normalize_all(unsigned int (&v)[NP], int N, cons
 	}
 }
 
-// ---------------------------------------------------------------------------------------------
-// Leftover list: pixels the register-resident rejection could not finish (more rejections than
-// its window holds, or more passes than it unrolls) are appended -- sorted column, result
-// address, layer -- to a device-global list and finished by k_stack_leftover, one pixel per
-// thread with full warps.  A typical deep-sky stack parks well under 1 % of its pixels here.
-// ---------------------------------------------------------------------------------------------
-struct LeftoverList {
-	unsigned int *count;		// items appended (may exceed capacity: the excess was handled in place)
-	unsigned int capacity;
-	uint4 *cols;			// [capacity][NP * 2 bytes]: the sorted column of each item, contiguous
-	uint2 *meta;			// [capacity]: result element index, layer
-};
-
+#ifndef SSC_SIGMA_REG_PASSES
+#define SSC_SIGMA_REG_PASSES 4	// clipping passes unrolled in registers before a pixel goes to the leftover list
+#endif
 enum { MODE_MEDIAN = 0, MODE_NOREJ = 1, MODE_SIGMA_REG = 2, MODE_QUEUE = 3 };
 
 // FULL: n_frames == NP (no sentinel padding, no per-frame bound checks in the unrolled code)
@@ -272,8 +210,8 @@ k_stack_fast(StackParams p, LeftoverList list) {
 			unsigned int rl[2] = {0, 0}, rh[2] = {0, 0};
 			bool done[2] = {false, false}, punt[2] = {false, false};
 #pragma unroll 1
-			for (int it = 0; it < 5; it++) {
-				if (it == 4) {			// a fifth pass would be needed
+			for (int it = 0; it <= SSC_SIGMA_REG_PASSES; it++) {
+				if (it == SSC_SIGMA_REG_PASSES) {	// one more pass would be needed
 					punt[0] = !done[0];
 					punt[1] = !done[1];
 					break;
@@ -291,21 +229,27 @@ k_stack_fast(StackParams p, LeftoverList list) {
 						if (lhs == k) ml = e;
 						if (rhs == k) mr = e;
 					}
-					const double median = lhs == rhs ? (double) (int) ml : dmul((double) (int) (ml + mr), 0.5);
-					const double tl = dmul(p.sig_low, sigma), th = dmul(p.sig_high, sigma);
+					// sigma_clipping (:1152,1156) in integers: the median is M2 / 2 with M2 an integer and the
+					// sample e an integer, so (median - e) is exact in FP64 and
+					//   median - e > tl  <=>  M2 - 2e > 2 tl  <=>  M2 - 2e > floor(2 tl)      (tl >= 0)
+					// and likewise on the high side: one float-to-int conversion per pass and side instead
+					// of a conversion, a subtraction and a compare per candidate.
+					const int M2 = lhs == rhs ? 2 * (int) ml : (int) (ml + mr);
+					const int TL = __double2int_rd(fmin(dmul(2.0, dmul(p.sig_low, sigma)), 1073741824.0));
+					const int TH = __double2int_rd(fmin(dmul(2.0, dmul(p.sig_high, sigma)), 1073741824.0));
 					int n = 0;
 #pragma unroll
-					for (int k = 0; k < 3; k++) {		// low candidates, in scan order (sigma_clipping, :1152)
+					for (int k = 0; k < 3; k++) {		// low candidates, in scan order
 						const unsigned int e = h ? v[k] >> 16 : v[k] & 0xFFFFu;
-						if (nl[h] == k && dsub(median, (double) (int) e) > tl) {
+						if (nl[h] == k && M2 - 2 * (int) e > TL) {
 							nl[h]++; n++; rl[h]++;
 							S[h] -= e; Q[h] -= (unsigned long long) e * e;
 						}
 					}
 #pragma unroll
-					for (int k = 0; k < 6; k++) {		// high candidates, from the top (:1156)
+					for (int k = 0; k < 6; k++) {		// high candidates, from the top
 						const unsigned int e = h ? v[NP - 1 - k] >> 16 : v[NP - 1 - k] & 0xFFFFu;
-						if (nh[h] == k && dsub((double) (int) e, median) > th) {
+						if (nh[h] == k && 2 * (int) e - M2 > TH) {
 							nh[h]++; n++; rh[h]++;
 							S[h] -= e; Q[h] -= (unsigned long long) e * e;
 						}
@@ -456,58 +400,6 @@ k_stack_fast(StackParams p, LeftoverList list) {
 		atomicAdd(&p.counters[tid], blk_counters[tid]);
 }
 
-// The leftover list, one pixel per thread: the column is already sorted, the sums are rebuilt.
-template <int NP>
-__global__ void __launch_bounds__(128)
-k_stack_leftover(StackParams p, LeftoverList list) {
-	__shared__ WORD col[NP * 128];
-	__shared__ double s_unbias[65], s_inv_n[65], s_inv_n2[65];
-	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
-	const int tid = threadIdx.x;
-	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
-	if (tid >= 1 && tid <= 64) {
-		s_unbias[tid] = tid > 1 ? ddiv((double) tid, (double) (tid - 1)) : 0.0;
-		s_inv_n[tid] = ddiv(1.0, (double) tid);
-		s_inv_n2[tid] = ddiv(1.0, (double) (tid * tid));
-	}
-	const SmallN tables{s_unbias, s_inv_n, s_inv_n2};
-	__syncthreads();
-	unsigned int n_items = *list.count;
-	if (n_items > list.capacity) n_items = list.capacity;
-	for (unsigned int base = blockIdx.x * 128; base < n_items; base += gridDim.x * 128) {
-		const unsigned int i = base + tid;
-		if (i < n_items) {
-			Column c{col + tid, 128};
-			const uint4 *src = list.cols + (size_t) i * (NP / 8);
-			unsigned long long S = 0, Q = 0;
-#pragma unroll
-			for (int q = 0; q < NP / 8; q++) {
-				const uint4 w = src[q];
-				const unsigned int ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					const unsigned int a = ww[k] & 0xFFFFu, bq = ww[k] >> 16;
-					c.set(8 * q + 2 * k, a);
-					c.set(8 * q + 2 * k + 1, bq);
-					S += a + bq;
-					Q += sq(a) + sq(bq);
-				}
-			}
-			RejectState ist{0, 0, 0, 0};
-			const unsigned int r = reject_sorted_and_mean<true>(c, NP, p.rejection, p.sig_low, p.sig_high, S, Q, ist, &tables);
-			const uint2 m = list.meta[i];
-			p.out[m.x] = (WORD) r;
-			if (ist.rej_lo) atomicAdd(&blk_counters[m.y * 2 + 0], (unsigned long long) ist.rej_lo);
-			if (ist.rej_hi) atomicAdd(&blk_counters[m.y * 2 + 1], (unsigned long long) ist.rej_hi);
-			if (ist.guard) atomicAdd(&blk_counters[6], 1ull);
-			if (ist.cap) atomicAdd(&blk_counters[7], 1ull);
-		}
-	}
-	__syncthreads();
-	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
-		atomicAdd(&p.counters[tid], blk_counters[tid]);
-}
-
 // The register-network kernel applies when two adjacent pixels can be fetched as one
 // aligned 32-bit word from every frame and nothing shifts the frames against each other.
 bool fast_path_eligible(const StackParams &p, int is_median) {
@@ -518,42 +410,6 @@ bool fast_path_eligible(const StackParams &p, int is_median) {
 	if (((uintptr_t) b.frames & 3) || ((uintptr_t) p.out & 3) || (p.out_layer_stride & 1)) return false;
 	if ((size_t) b.layers * p.out_layer_stride >= 0xFFFFFFF0ull) return false;	// 32-bit result indices
 	return true;
-}
-
-// Leftover-list storage, kept per device between launches (grown on demand; the first launch of
-// a larger shape allocates, i.e. synchronises once).
-struct LeftoverStore {
-	unsigned int *count = nullptr;
-	void *cols = nullptr;
-	void *meta = nullptr;
-	size_t capacity = 0, col_bytes = 0;
-};
-static LeftoverStore g_leftover[64];
-
-static int leftover_list(int np, unsigned long long pixels, LeftoverList &list, cudaStream_t stream) {
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (dev < 0 || dev >= 64) return SSC_ERR_ARG;
-	LeftoverStore &st = g_leftover[dev];
-	size_t want = (size_t) (pixels / 16) + 65536;	// 6 % of the pixels; beyond that pixels finish in place
-	if (want > 0x7FFFFFF0ull) want = 0x7FFFFFF0ull;
-	if (!st.count && cudaMalloc(&st.count, sizeof(unsigned int)) != cudaSuccess) return SSC_ERR_CUDA;
-	if (st.capacity < want || st.col_bytes < (size_t) np * 2) {
-		if (st.cols) cudaFree(st.cols);
-		if (st.meta) cudaFree(st.meta);
-		st.cols = st.meta = nullptr;
-		st.capacity = 0;
-		if (cudaMalloc(&st.cols, want * 128) != cudaSuccess) return SSC_ERR_CUDA;	// room for 64-frame columns
-		if (cudaMalloc(&st.meta, want * sizeof(uint2)) != cudaSuccess) return SSC_ERR_CUDA;
-		st.capacity = want;
-		st.col_bytes = 128;
-	}
-	if (cudaMemsetAsync(st.count, 0, sizeof(unsigned int), stream) != cudaSuccess) return SSC_ERR_CUDA;
-	list.count = st.count;
-	list.capacity = (unsigned int) st.capacity;
-	list.cols = (uint4 *) st.cols;
-	list.meta = (uint2 *) st.meta;
-	return SSC_OK;
 }
 
 template <int NP, bool FULL, int MODE>
@@ -573,13 +429,7 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 	}
 	k_stack_fast<NP, FULL, MODE><<<(unsigned int) blocks, FAST_THREADS, smem, stream>>>(p, list);
 	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
-	if constexpr (MODE == MODE_SIGMA_REG) {
-		int dev = 0, sms = 148;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		k_stack_leftover<NP><<<sms * 8, 128, 0, stream>>>(p, list);
-		if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
-	}
+	if constexpr (MODE == MODE_SIGMA_REG) return launch_leftover<NP>(p, list, stream);
 	return SSC_OK;
 }
 

@@ -139,7 +139,9 @@ int launch_stack_generic(const StackParams &p, const unsigned int *list, const u
 int g_kernel_path = 0;
 
 int launch_stack(const StackParams &p, int is_median, cudaStream_t stream) {
-	if (g_kernel_path == 0 && fast_path_eligible(p, is_median))
+	if (g_kernel_path == 2 && pipe_path_eligible(p, is_median))
+		return launch_stack_pipe(p, stream);	// experimental (slower than the register kernel so far)
+	if (g_kernel_path != 1 && fast_path_eligible(p, is_median))
 		return launch_stack_fast(p, is_median, stream);
 	return launch_stack_generic(p, nullptr, nullptr, 0, is_median, stream);
 }

@@ -251,7 +251,7 @@ def test_register_network_kernel_equals_general_kernel(gpu, port, rej, n, norm):
     columns) must be interchangeable: same image, counters and guard events, both equal to the oracle."""
     fr = synth.make_frames(n, 1, 24, 64, seed=n + norm, outlier_p=8e-3, zero_p=2e-3, stars=3)
     outs = []
-    for path in (0, 1):
+    for path in (0, 1, 2):                                   # automatic, general kernel, pipeline kernel where eligible
         gpu.set_kernel_path(path)
         try:
             if rej == "median":
@@ -262,9 +262,10 @@ def test_register_network_kernel_equals_general_kernel(gpu, port, rej, n, norm):
         finally:
             gpu.set_kernel_path(0)
         outs.append(res)
-    a, b = outs
-    assert np.array_equal(a.data, b.data)
-    assert np.array_equal(a.irej, b.irej) and a.guard_fired == b.guard_fired and a.cap_hit == b.cap_hit
+    a = outs[0]
+    for b in outs[1:]:
+        assert np.array_equal(a.data, b.data)
+        assert np.array_equal(a.irej, b.irej) and a.guard_fired == b.guard_fired and a.cap_hit == b.cap_hit
     if rej == "median":
         assert np.array_equal(a.data, port.stack_median(fr, normalize=norm, coeff=a.coeff)["out"])
     else:

@@ -21,12 +21,15 @@ def main():
     ap.add_argument("--normalize", type=int, default=2)
     ap.add_argument("--median", action="store_true")
     ap.add_argument("--generic", action="store_true")
+    ap.add_argument("--path", type=int, default=0, help="ssc_set_kernel_path: 0 auto, 1 general, 2 pipeline kernel")
     a = ap.parse_args()
     import torch
     import __graft_entry__ as ge
     pkg = ge.load_package()
     if a.generic:
         pkg.set_kernel_path(1)
+    elif a.path:
+        pkg.set_kernel_path(a.path)
     n, c, h, w = a.frames, a.layers, a.rows, a.width
     dev = torch.device("cuda", 0)
     sp = torch.cuda.current_stream().cuda_stream
