@@ -48,17 +48,25 @@ k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
 		if (vec_ok) {
 			const size_t nvec = (end - beg) >> 3;
 			const uint4 *v4 = reinterpret_cast<const uint4 *>(src + beg);
-			for (size_t i = threadIdx.x; i < nvec; i += HIST_THREADS) {
-				uint4 v = __ldg(v4 + i);
-				unsigned int w[4] = {v.x, v.y, v.z, v.w};
+			auto count8 = [&](const uint4 &v) {
+				const unsigned int w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
-					unsigned int a = w[k] & 0xFFFFu, c = w[k] >> 16;
+					const unsigned int a = w[k] & 0xFFFFu, c = w[k] >> 16;
 					atomicAdd(&sh[a >> 1], 1u << ((a & 1) * 16));
 					atomicAdd(&sh[c >> 1], 1u << ((c & 1) * 16));
 					seen |= a | c;
 				}
+			};
+			// four 16-byte loads in flight per thread (64 KB per SM): the kernel is otherwise bound by
+			// HBM latency, not by the shared-memory atomics
+			size_t i = threadIdx.x;
+			for (; i + 3 * HIST_THREADS < nvec; i += 4 * HIST_THREADS) {
+				const uint4 v0 = __ldg(v4 + i), v1 = __ldg(v4 + i + HIST_THREADS);
+				const uint4 v2 = __ldg(v4 + i + 2 * HIST_THREADS), v3 = __ldg(v4 + i + 3 * HIST_THREADS);
+				count8(v0); count8(v1); count8(v2); count8(v3);
 			}
+			for (; i < nvec; i += HIST_THREADS) count8(__ldg(v4 + i));
 			for (size_t i = beg + (nvec << 3) + threadIdx.x; i < end; i += HIST_THREADS) {
 				unsigned int a = src[i];
 				atomicAdd(&sh[a >> 1], 1u << ((a & 1) * 16));
