@@ -55,7 +55,7 @@ constexpr int FAST_THREADS = 128;
 
 template <int NP, bool FULL, int MODE>
 __global__ void __launch_bounds__(FAST_THREADS, 4)
-k_stack_fast(StackParams p, LeftoverList list) {
+k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	extern __shared__ unsigned int cols[];		// [NP][FAST_THREADS] packed columns
 	__shared__ double s_coef[3 * 64];
 	__shared__ double s_unbias[65], s_inv_n[65], s_inv_n2[65];	// small-n tables (ssc_device.cuh)
@@ -94,7 +94,10 @@ k_stack_fast(StackParams p, LeftoverList list) {
 	__syncthreads();
 
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * W2;
-	unsigned long long g = (unsigned long long) blockIdx.x * FAST_THREADS + tid;
+	// Blocks loop over tiles (the launcher bounds the grid): the tables, the coefficient copy and
+	// their barriers above are paid once per block instead of once per tile.
+	for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+	unsigned long long g = tile * FAST_THREADS + tid;
 	const bool active = g < total;
 	if (!active) g = total - 1;
 	const int x2 = (int) (g % W2);
@@ -165,7 +168,7 @@ k_stack_fast(StackParams p, LeftoverList list) {
 		res[0] = ((lo & 0xFFFFu) + (hi & 0xFFFFu)) >> 1;
 		res[1] = ((lo >> 16) + (hi >> 16)) >> 1;
 		if (active) *reinterpret_cast<unsigned int *>(dst) = res[0] | (res[1] << 16);
-		return;
+		continue;
 	} else {
 		// exact integer sums of the (normalized) samples; the sum fits 32 bits and comes straight
 		// from the packed words (IDP.2A: acc + lo16 * 1 + hi16 * 0), the sum of squares needs 64
@@ -194,7 +197,7 @@ k_stack_fast(StackParams p, LeftoverList list) {
 			res[0] = mean_to_word<true>(S[0], N, &tables);
 			res[1] = mean_to_word<true>(S[1], N, &tables);
 			if (active) *reinterpret_cast<unsigned int *>(dst) = res[0] | (res[1] << 16);
-			return;
+			continue;
 		} else if constexpr (MODE == MODE_SIGMA_REG) {
 			// ---- sigma clipping (stacking.c:1674-1695) entirely in registers.  In a sorted stack the
 			// low flags are a prefix and the high flags a suffix, the survivors stay [nl, NP - nh), and
@@ -395,6 +398,8 @@ k_stack_fast(StackParams p, LeftoverList list) {
 			if (active) *reinterpret_cast<unsigned int *>(dst) = res[0] | (res[1] << 16);
 		}
 	}
+	if (MODE == MODE_QUEUE || MODE == MODE_SIGMA_REG) __syncthreads();	// shared-memory columns / queue are reused by the next tile
+	}	// tiles
 	__syncthreads();
 	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
 		atomicAdd(&p.counters[tid], blk_counters[tid]);
@@ -420,14 +425,26 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 	const size_t smem = (size_t) NP * FAST_THREADS * sizeof(unsigned int);
 	if (cudaFuncSetAttribute(k_stack_fast<NP, FULL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
-	const unsigned long long blocks = (total + FAST_THREADS - 1) / FAST_THREADS;
-	if (blocks > 0x7FFFFFFFull) return SSC_ERR_ARG;
+	const unsigned long long tiles = (total + FAST_THREADS - 1) / FAST_THREADS;
+	if (tiles > 0x7FFFFFFFull) return SSC_ERR_ARG;
+	unsigned long long blocks = tiles;
+	{	// a bounded grid of looping blocks: 16 per resident slot measured best (SSC_FAST_WAVES overrides)
+		int dev = 0, sms = 148, per_sm = 1;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stack_fast<NP, FULL, MODE>, FAST_THREADS, smem) != cudaSuccess || per_sm < 1)
+			per_sm = 1;
+		static int waves = 0;
+		if (!waves) { const char *e = getenv("SSC_FAST_WAVES"); waves = e ? atoi(e) : 16; if (waves < 1) waves = 1; }
+		const unsigned long long cap = (unsigned long long) sms * per_sm * waves;
+		if (blocks > cap) blocks = cap;
+	}
 	LeftoverList list{nullptr, 0, nullptr, nullptr};
 	if (MODE == MODE_SIGMA_REG) {
 		int rc = leftover_list(NP, total * 2, list, stream);
 		if (rc) return rc;
 	}
-	k_stack_fast<NP, FULL, MODE><<<(unsigned int) blocks, FAST_THREADS, smem, stream>>>(p, list);
+	k_stack_fast<NP, FULL, MODE><<<(unsigned int) blocks, FAST_THREADS, smem, stream>>>(p, list, (unsigned int) tiles);
 	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
 	if constexpr (MODE == MODE_SIGMA_REG) return launch_leftover<NP>(p, list, stream);
 	return SSC_OK;
