@@ -23,77 +23,95 @@ namespace ssc {
 // values per chunk, not with the number of samples.
 // ---------------------------------------------------------------------------
 constexpr int HIST_THREADS = 1024;
-constexpr int HIST_CHUNK = 65528;	// multiple of 8, < 65536
+constexpr int HIST_DEPTH = 3;
+constexpr int HIST_GROUPS_PER_FLUSH = 2;
 
 __global__ void __launch_bounds__(HIST_THREADS, 1)
 k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
-	extern __shared__ uint32_t sh[];	// 32768 words
+	extern __shared__ __align__(16) uint32_t sh[];	// 32768 words: 65536 packed 16-bit counters
 	__shared__ unsigned int any_gt255;
 	const int frame = blockIdx.x / ctas_per_frame;
 	const int part = blockIdx.x % ctas_per_frame;
+	const int tid = threadIdx.x;
 	const size_t band_px = (size_t) b.out_rows * b.width;	// layer-0 samples of this band
 	const WORD *src = b.frames + (size_t) frame * b.frame_stride + (size_t) (b.out_row0 - b.buf_row0) * b.width;
 	uint32_t *gh = hist + (size_t) frame * SSC_HIST_STRIDE;
-	const bool vec_ok = ((uintptr_t) src % 16 == 0);
 
-	for (int i = threadIdx.x; i < 32768; i += HIST_THREADS) sh[i] = 0;
-	if (threadIdx.x == 0) any_gt255 = 0;
+	for (int i = tid; i < 32768; i += HIST_THREADS) sh[i] = 0;
+	if (tid == 0) any_gt255 = 0;
 	__syncthreads();
 
 	unsigned int seen = 0;
-	const size_t n_chunks = (band_px + HIST_CHUNK - 1) / HIST_CHUNK;
-	for (size_t ch = part; ch < n_chunks; ch += ctas_per_frame) {
-		const size_t beg = ch * HIST_CHUNK;
-		const size_t end = beg + HIST_CHUNK < band_px ? beg + HIST_CHUNK : band_px;
-		if (vec_ok) {
-			const size_t nvec = (end - beg) >> 3;
-			const uint4 *v4 = reinterpret_cast<const uint4 *>(src + beg);
-			auto count8 = [&](const uint4 &v) {
-				const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+	auto count1 = [&](unsigned int a) {
+		atomicAdd(&sh[a >> 1], 1u << ((a & 1) * 16));
+		seen |= a;
+	};
+	auto count8 = [&](const uint4 &v) {
+		const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			count1(w[k] & 0xFFFFu);
+			count1(w[k] >> 16);
+		}
+	};
+	auto flush = [&]() {	// non-zero words -> the global 32-bit histogram; 16-byte scans of the table
+		__syncthreads();
+		uint4 *sh4 = reinterpret_cast<uint4 *>(sh);
+		for (int i = tid; i < 8192; i += HIST_THREADS) {
+			const uint4 q = sh4[i];
+			if (q.x | q.y | q.z | q.w) {
+				sh4[i] = make_uint4(0, 0, 0, 0);
+				const unsigned int w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
-					const unsigned int a = w[k] & 0xFFFFu, c = w[k] >> 16;
-					atomicAdd(&sh[a >> 1], 1u << ((a & 1) * 16));
-					atomicAdd(&sh[c >> 1], 1u << ((c & 1) * 16));
-					seen |= a | c;
+					if (w[k] & 0xFFFFu) atomicAdd(&gh[8 * i + 2 * k], w[k] & 0xFFFFu);
+					if (w[k] >> 16) atomicAdd(&gh[8 * i + 2 * k + 1], w[k] >> 16);
 				}
-			};
-			// four 16-byte loads in flight per thread (64 KB per SM): the kernel is otherwise bound by
-			// HBM latency, not by the shared-memory atomics
-			size_t i = threadIdx.x;
-			for (; i + 3 * HIST_THREADS < nvec; i += 4 * HIST_THREADS) {
-				const uint4 v0 = __ldg(v4 + i), v1 = __ldg(v4 + i + HIST_THREADS);
-				const uint4 v2 = __ldg(v4 + i + 2 * HIST_THREADS), v3 = __ldg(v4 + i + 3 * HIST_THREADS);
-				count8(v0); count8(v1); count8(v2); count8(v3);
-			}
-			for (; i < nvec; i += HIST_THREADS) count8(__ldg(v4 + i));
-			for (size_t i = beg + (nvec << 3) + threadIdx.x; i < end; i += HIST_THREADS) {
-				unsigned int a = src[i];
-				atomicAdd(&sh[a >> 1], 1u << ((a & 1) * 16));
-				seen |= a;
-			}
-		} else {
-			for (size_t i = beg + threadIdx.x; i < end; i += HIST_THREADS) {
-				unsigned int a = src[i];
-				atomicAdd(&sh[a >> 1], 1u << ((a & 1) * 16));
-				seen |= a;
 			}
 		}
 		__syncthreads();
-		for (int i = threadIdx.x; i < 32768; i += HIST_THREADS) {
-			uint32_t w = sh[i];
-			if (w) {
-				sh[i] = 0;
-				if (w & 0xFFFFu) atomicAdd(&gh[2 * i], w & 0xFFFFu);
-				if (w >> 16) atomicAdd(&gh[2 * i + 1], w >> 16);
-			}
-		}
-		__syncthreads();
+	};
+
+	// this block's contiguous share of the frame's band, in 16-byte vectors (head and tail samples
+	// that do not fall on a vector are left to part 0 below)
+	const size_t head = ((16 - ((uintptr_t) src & 15)) & 15) >> 1;		// samples before the first aligned vector
+	const size_t lead = head < band_px ? head : band_px;
+	const size_t nvec_all = (band_px - lead) >> 3;
+	const size_t v_beg = nvec_all * part / ctas_per_frame, v_end = nvec_all * (part + 1) / ctas_per_frame;
+	const uint4 *v4 = reinterpret_cast<const uint4 *>(src + lead);
+
+	// Software pipeline, HIST_DEPTH 16-byte loads in flight per thread (48 KB per SM): the loads of
+	// the next group are issued before the current group's shared-memory atomics and stay in flight
+	// across a flush, so neither HBM latency nor the flush barriers are exposed.  A flush every
+	// HIST_GROUPS_PER_FLUSH groups: 2 * 3 * 1024 * 8 = 49152 samples, below the 16-bit counter range.
+	uint4 q[HIST_DEPTH];
+#pragma unroll
+	for (int k = 0; k < HIST_DEPTH; k++) {
+		const size_t idx = v_beg + tid + (size_t) k * HIST_THREADS;
+		q[k] = idx < v_end ? __ldg(v4 + idx) : make_uint4(0, 0, 0, 0);
 	}
+	const size_t per_group = (size_t) HIST_DEPTH * HIST_THREADS;
+	const size_t n_groups = (v_end - v_beg + per_group - 1) / per_group;	// block-uniform
+	for (size_t g = 0; g < n_groups; g++) {
+#pragma unroll
+		for (int k = 0; k < HIST_DEPTH; k++) {
+			const size_t idx = v_beg + tid + (g * HIST_DEPTH + k) * HIST_THREADS;
+			const uint4 v = q[k];
+			const size_t nxt = idx + per_group;
+			q[k] = nxt < v_end ? __ldg(v4 + nxt) : make_uint4(0, 0, 0, 0);
+			if (idx < v_end) count8(v);
+		}
+		if ((g + 1) % HIST_GROUPS_PER_FLUSH == 0) flush();
+	}
+	if (part == 0) {	// the few samples outside the vectors
+		for (size_t i = tid; i < lead; i += HIST_THREADS) count1(src[i]);
+		for (size_t i = lead + (nvec_all << 3) + tid; i < band_px; i += HIST_THREADS) count1(src[i]);
+	}
+	flush();
 	// word 65537: "layer 0 of this band has a sample > 255" (consumed by k_other_layers_gt255)
 	if (seen > 255u) atomicOr(&any_gt255, 1u);
 	__syncthreads();
-	if (threadIdx.x == 0 && any_gt255) atomicOr(&gh[65537], 1u);
+	if (tid == 0 && any_gt255) atomicOr(&gh[65537], 1u);
 }
 
 // get_normalized_value (src/core/utils.c:454-459) looks at the max over ALL
@@ -124,11 +142,11 @@ int launch_histogram(const ssc_band &b, uint32_t *hist, cudaStream_t stream) {
 	if (cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4) != cudaSuccess)
 		return SSC_ERR_CUDA;
 	const size_t band_px = (size_t) b.out_rows * b.width;
-	const size_t n_chunks = (band_px + HIST_CHUNK - 1) / HIST_CHUNK;
 	// one CTA per SM is resident (128 KB of shared memory): spread every frame over
-	// enough CTAs to fill the machine about twice
+	// enough CTAs to fill the machine about twice, but keep at least ~32K samples per CTA
 	int per_frame = (2 * sms + b.n_frames - 1) / b.n_frames;
-	if ((size_t) per_frame > n_chunks) per_frame = (int) n_chunks;
+	const size_t max_parts = band_px / 32768 + 1;
+	if ((size_t) per_frame > max_parts) per_frame = (int) max_parts;
 	if (per_frame < 1) per_frame = 1;
 	k_histogram<<<b.n_frames * per_frame, HIST_THREADS, 32768 * 4, stream>>>(b, hist, per_frame);
 	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
