@@ -15,35 +15,81 @@ namespace ssc {
 // ---------------------------------------------------------------------------
 // K4: histogram of layer 0 of every frame of a band.
 //
-// A CTA owns a shared-memory histogram of all 65536 bins as 16-bit counters
-// packed two per word (128 KB).  It consumes its frame's rows in chunks of at
-// most 65535 samples -- a 16-bit counter cannot overflow within a chunk
-// whatever the data -- then flushes the non-zero words to the global 32-bit
-// histogram.  Global atomics therefore scale with the number of DISTINCT
-// values per chunk, not with the number of samples.
+// A CTA owns two shared-memory tables:
+//   * full: all 65536 bins as 16-bit counters packed two per word (128 KB).  A 16-bit counter
+//           cannot overflow before the CTA has put 65536 samples into the table, so the table is
+//           flushed to the global 32-bit histogram whenever that could happen next;
+//   * win:  32-bit counters for a 2048-bin window around the block's typical sample value (8 KB),
+//           never flushed before the end.
+// The background of an astronomical frame is narrow, so almost every sample lands in the window
+// and the flush of the full table (8192 16-byte reads and two barriers) becomes rare; with
+// wide-range data everything goes through the full table -- same result either way.
+// Global atomics scale with the number of DISTINCT values, not with the samples.
+// Measured (profiles/r01_ncu_histogram.txt): the kernel is bound by the shared-memory atomic unit
+// (a warp's ATOMS costs 4-5 wavefronts whatever the bank pattern: a lane-private, conflict-free
+// window table measured no faster, and neither did flushing less often), not by HBM.
 // ---------------------------------------------------------------------------
 constexpr int HIST_THREADS = 1024;
 constexpr int HIST_DEPTH = 3;
-constexpr int HIST_GROUPS_PER_FLUSH = 2;
+constexpr int HIST_WIN = 2048;				// bins in the 32-bit window
+constexpr unsigned int HIST_GROUP_SAMPLES = HIST_DEPTH * HIST_THREADS * 8;	// 24576
+constexpr size_t HIST_SMEM = (32768 + HIST_WIN) * sizeof(uint32_t);
 
 __global__ void __launch_bounds__(HIST_THREADS, 1)
 k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
-	extern __shared__ __align__(16) uint32_t sh[];	// 32768 words: 65536 packed 16-bit counters
-	__shared__ unsigned int any_gt255;
+	extern __shared__ __align__(16) uint32_t sh[];	// full[32768], then win[HIST_WIN]
+	__shared__ unsigned int any_gt255, s_base, s_outside[2], s_acc[32];
 	const int frame = blockIdx.x / ctas_per_frame;
 	const int part = blockIdx.x % ctas_per_frame;
-	const int tid = threadIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31;
 	const size_t band_px = (size_t) b.out_rows * b.width;	// layer-0 samples of this band
 	const WORD *src = b.frames + (size_t) frame * b.frame_stride + (size_t) (b.out_row0 - b.buf_row0) * b.width;
 	uint32_t *gh = hist + (size_t) frame * SSC_HIST_STRIDE;
 
-	for (int i = tid; i < 32768; i += HIST_THREADS) sh[i] = 0;
-	if (tid == 0) any_gt255 = 0;
-	__syncthreads();
+	for (int i = tid; i < 32768 + HIST_WIN; i += HIST_THREADS) sh[i] = 0;
+	if (tid == 0) { any_gt255 = 0; s_outside[0] = s_outside[1] = 0; }
 
-	unsigned int seen = 0;
-	auto count1 = [&](unsigned int a) {
-		atomicAdd(&sh[a >> 1], 1u << ((a & 1) * 16));
+	// this block's contiguous share of the frame's band, in 16-byte vectors (head and tail samples
+	// that do not fall on a vector are left to part 0 below)
+	const size_t head = ((16 - ((uintptr_t) src & 15)) & 15) >> 1;		// samples before the first aligned vector
+	const size_t lead = head < band_px ? head : band_px;
+	const size_t nvec_all = (band_px - lead) >> 3;
+	const size_t v_beg = nvec_all * part / ctas_per_frame, v_end = nvec_all * (part + 1) / ctas_per_frame;
+	const uint4 *v4 = reinterpret_cast<const uint4 *>(src + lead);
+
+	uint4 q[HIST_DEPTH];
+#pragma unroll
+	for (int k = 0; k < HIST_DEPTH; k++) {
+		const size_t idx = v_beg + tid + (size_t) k * HIST_THREADS;
+		q[k] = idx < v_end ? __ldg(v4 + idx) : make_uint4(0, 0, 0, 0);
+	}
+
+	// window position: the mean of one sample per thread (any position gives the right histogram)
+	{
+		const bool have = v_beg + tid < v_end;
+		const unsigned int probe = __reduce_add_sync(0xffffffffu, have ? (q[0].x & 0xFFFFu) : 0u);
+		const unsigned int cnt = __reduce_add_sync(0xffffffffu, have ? 1u : 0u);
+		if (lane == 0) s_acc[tid >> 5] = cnt ? probe / cnt : 0xFFFFFFFFu;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		unsigned int m = 0, k = 0;
+		for (int i = 0; i < HIST_THREADS / 32; i++)
+			if (s_acc[i] != 0xFFFFFFFFu) { m += s_acc[i]; k++; }
+		int base = (int) (k ? m / k : 0u) - HIST_WIN / 2;
+		if (base < 0) base = 0;
+		if (base > 65536 - HIST_WIN) base = 65536 - HIST_WIN;
+		s_base = (unsigned int) base;
+	}
+	__syncthreads();
+	const unsigned int base = s_base;
+
+	unsigned int seen = 0, outside = 0;
+	auto count1 = [&](unsigned int a) {	// one atomic, no divergence
+		const unsigned int d = a - base;
+		const bool in = d < (unsigned int) HIST_WIN;
+		atomicAdd(&sh[in ? 32768u + d : a >> 1], in ? 1u : 1u << ((a & 1) * 16));
+		outside += in ? 0u : 1u;
 		seen |= a;
 	};
 	auto count8 = [&](const uint4 &v) {
@@ -54,14 +100,14 @@ k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
 			count1(w[k] >> 16);
 		}
 	};
-	auto flush = [&]() {	// non-zero words -> the global 32-bit histogram; 16-byte scans of the table
+	auto flush_full = [&]() {	// non-zero 16-bit counters -> the global 32-bit histogram
 		__syncthreads();
 		uint4 *sh4 = reinterpret_cast<uint4 *>(sh);
 		for (int i = tid; i < 8192; i += HIST_THREADS) {
-			const uint4 q = sh4[i];
-			if (q.x | q.y | q.z | q.w) {
+			const uint4 x = sh4[i];
+			if (x.x | x.y | x.z | x.w) {
 				sh4[i] = make_uint4(0, 0, 0, 0);
-				const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+				const unsigned int w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
 					if (w[k] & 0xFFFFu) atomicAdd(&gh[8 * i + 2 * k], w[k] & 0xFFFFu);
@@ -72,26 +118,12 @@ k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
 		__syncthreads();
 	};
 
-	// this block's contiguous share of the frame's band, in 16-byte vectors (head and tail samples
-	// that do not fall on a vector are left to part 0 below)
-	const size_t head = ((16 - ((uintptr_t) src & 15)) & 15) >> 1;		// samples before the first aligned vector
-	const size_t lead = head < band_px ? head : band_px;
-	const size_t nvec_all = (band_px - lead) >> 3;
-	const size_t v_beg = nvec_all * part / ctas_per_frame, v_end = nvec_all * (part + 1) / ctas_per_frame;
-	const uint4 *v4 = reinterpret_cast<const uint4 *>(src + lead);
-
 	// Software pipeline, HIST_DEPTH 16-byte loads in flight per thread (48 KB per SM): the loads of
 	// the next group are issued before the current group's shared-memory atomics and stay in flight
-	// across a flush, so neither HBM latency nor the flush barriers are exposed.  A flush every
-	// HIST_GROUPS_PER_FLUSH groups: 2 * 3 * 1024 * 8 = 49152 samples, below the 16-bit counter range.
-	uint4 q[HIST_DEPTH];
-#pragma unroll
-	for (int k = 0; k < HIST_DEPTH; k++) {
-		const size_t idx = v_beg + tid + (size_t) k * HIST_THREADS;
-		q[k] = idx < v_end ? __ldg(v4 + idx) : make_uint4(0, 0, 0, 0);
-	}
+	// across a flush.
 	const size_t per_group = (size_t) HIST_DEPTH * HIST_THREADS;
 	const size_t n_groups = (v_end - v_beg + per_group - 1) / per_group;	// block-uniform
+	unsigned int in_full = 0, prev[2] = {0, 0};
 	for (size_t g = 0; g < n_groups; g++) {
 #pragma unroll
 		for (int k = 0; k < HIST_DEPTH; k++) {
@@ -101,13 +133,30 @@ k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
 			q[k] = nxt < v_end ? __ldg(v4 + nxt) : make_uint4(0, 0, 0, 0);
 			if (idx < v_end) count8(v);
 		}
-		if ((g + 1) % HIST_GROUPS_PER_FLUSH == 0) flush();
+		// Samples this CTA has put into the full table since its last flush.  Two monotonic
+		// counters used alternately: a warp already in group g+1 adds to the other one, so every
+		// thread reads the same value here and the flush decision is block-uniform.
+		const unsigned int w_out = __reduce_add_sync(0xffffffffu, outside);
+		outside = 0;
+		if (lane == 0 && w_out) atomicAdd(&s_outside[g & 1], w_out);
+		__syncthreads();
+		const unsigned int t = s_outside[g & 1];
+		in_full += t - prev[g & 1];
+		prev[g & 1] = t;
+		if (in_full + HIST_GROUP_SAMPLES + 16 > 65535u) {	// the next group could overflow a counter
+			flush_full();
+			in_full = 0;
+		}
 	}
-	if (part == 0) {	// the few samples outside the vectors
+	if (part == 0) {	// the few (< 16) samples outside the vectors
 		for (size_t i = tid; i < lead; i += HIST_THREADS) count1(src[i]);
 		for (size_t i = lead + (nvec_all << 3) + tid; i < band_px; i += HIST_THREADS) count1(src[i]);
 	}
-	flush();
+	flush_full();
+	for (int i = tid; i < HIST_WIN; i += HIST_THREADS) {
+		const unsigned int c = sh[32768 + i];
+		if (c) atomicAdd(&gh[base + i], c);
+	}
 	// word 65537: "layer 0 of this band has a sample > 255" (consumed by k_other_layers_gt255)
 	if (seen > 255u) atomicOr(&any_gt255, 1u);
 	__syncthreads();
@@ -139,7 +188,7 @@ int launch_histogram(const ssc_band &b, uint32_t *hist, cudaStream_t stream) {
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	if (cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4) != cudaSuccess)
+	if (cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) HIST_SMEM) != cudaSuccess)
 		return SSC_ERR_CUDA;
 	const size_t band_px = (size_t) b.out_rows * b.width;
 	// one CTA per SM is resident (128 KB of shared memory): spread every frame over
@@ -148,7 +197,7 @@ int launch_histogram(const ssc_band &b, uint32_t *hist, cudaStream_t stream) {
 	const size_t max_parts = band_px / 32768 + 1;
 	if ((size_t) per_frame > max_parts) per_frame = (int) max_parts;
 	if (per_frame < 1) per_frame = 1;
-	k_histogram<<<b.n_frames * per_frame, HIST_THREADS, 32768 * 4, stream>>>(b, hist, per_frame);
+	k_histogram<<<b.n_frames * per_frame, HIST_THREADS, HIST_SMEM, stream>>>(b, hist, per_frame);
 	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
 	if (b.layers > 1) {
 		dim3 grid(8, b.n_frames);
