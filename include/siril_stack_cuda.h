@@ -172,6 +172,11 @@ int ssc_take_result(ssc_result *out);
 int ssc_stack_summing(struct stacking_args *args);
 int ssc_stack_median(struct stacking_args *args);
 int ssc_stack_mean_with_rejection(struct stacking_args *args);
+/* the other two entries of stacking_methods[] (stacking.c:54-56): stack_addmax (:824) and
+ * stack_addmin (:979); frames chosen by args->filtering_criterion like stack_summing,
+ * ssc_result.hi = the brightest / darkest result value as the reference leaves it in gfit.hi */
+int ssc_stack_addmax(struct stacking_args *args);
+int ssc_stack_addmin(struct stacking_args *args);
 /* compute_normalization (stacking.c:125): fills coeff->offset/mul/scale[nb_images_to_stack] */
 int ssc_compute_normalization(struct stacking_args *args, norm_coeff *coeff, normalization mode);
 
@@ -237,6 +242,12 @@ int ssc_dev_stack_mean(const ssc_band *band, int normalize, const double *coeff,
 int ssc_dev_sum_accumulate(const ssc_band *band, uint32_t *acc, unsigned long long *maxim, void *stream);
 int ssc_dev_sum_finish(const uint32_t *acc, size_t count, const unsigned long long *maxim,
 		WORD *out, void *stream);
+
+/* K1c: stack_addmax (take_max != 0) / stack_addmin in one pass (stacking.c:918-936, 1074-1092):
+ * out (device WORD [layers][out_rows][width]) = brightest / darkest sample per pixel;
+ * *extreme (device unsigned int; the caller sets 0 for max, 0xFFFF for min before the first
+ * band of an image) folds the max / min of the result (gfit.hi). */
+int ssc_dev_stack_extreme(const ssc_band *band, int take_max, WORD *out, unsigned int *extreme, void *stream);
 
 /* K4: exact 65536-bin histograms of layer 0 of every frame of the band
  * (replaces the sort in statistics.c:279-285).  hist: device uint32_t

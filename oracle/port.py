@@ -69,6 +69,15 @@ def stack_sum(frames, shiftx=None, shifty=None, row_order=0):
     return dict(out=out, retval=rv, maxim=mx.value)
 
 
+def stack_extreme(frames, take_max, shiftx=None, shifty=None, row_order=0):
+    """stack_addmax (take_max=True) / stack_addmin; 'hi' is what the reference leaves in gfit.hi."""
+    a, keep, (n, c, h, w) = _args(frames, 0, 0, (0, 0), None, shiftx, shifty, row_order, 0, 0)
+    out = np.zeros((c, h, w), np.uint16)
+    ex = C.c_uint16()
+    rv = lib().so_stack_extreme(C.byref(a), int(bool(take_max)), C.c_void_p(out.ctypes.data), C.byref(ex))
+    return dict(out=out, retval=rv, hi=ex.value)
+
+
 def stack_median(frames, normalize=NO_NORM, coeff=None, row_order=0, threads=0):
     a, keep, (n, c, h, w) = _args(frames, normalize, 0, (0, 0), coeff, None, None, row_order, 0, threads)
     out = np.zeros((c, h, w), np.uint16)

@@ -6,7 +6,7 @@
 #define OREF_API_H
 #include <stdint.h>
 
-enum { OREF_SUM = 0, OREF_MEAN = 1, OREF_MEDIAN = 2, OREF_NORMALIZATION_ONLY = 3 };
+enum { OREF_SUM = 0, OREF_MEAN = 1, OREF_MEDIAN = 2, OREF_NORMALIZATION_ONLY = 3, OREF_ADDMAX = 4, OREF_ADDMIN = 5 };
 
 typedef struct {
 	const unsigned short *frames;	/* [N][C][H][W] in storage order */
@@ -24,6 +24,7 @@ typedef struct {
 } oref_config;
 
 int oref_num_procs(void);
+int oref_last_hi(void);	/* gfit.hi after the last successful oref_run, -1 otherwise */
 /* out: [C][H][W]; irej: [3][2] low/high; coeff: [3][N] offset,mul,scale (may be NULL);
  * timing[0] = seconds in args->method(args), timing[1] = seconds in a separate
  * compute_normalization call (0 if not run separately). Returns the operator's retval. */

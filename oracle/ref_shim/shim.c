@@ -372,6 +372,12 @@ static double now_s(void) {
 	return tv.tv_sec + 1e-6 * tv.tv_usec;
 }
 
+static int last_hi = -1;
+/* gfit.hi as the last successful operator left it (sum, addmax, addmin set it) */
+int oref_last_hi(void) {
+	return last_hi;
+}
+
 int oref_num_procs(void) {
 #ifdef _OPENMP
 	return omp_get_num_procs();
@@ -485,6 +491,8 @@ int oref_run(const oref_config *cfg, unsigned short *out, uint64_t irej[6],
 	case OREF_SUM: args.method = stack_summing; break;
 	case OREF_MEAN: args.method = stack_mean_with_rejection; break;
 	case OREF_MEDIAN: args.method = stack_median; break;
+	case OREF_ADDMAX: args.method = stack_addmax; break;
+	case OREF_ADDMIN: args.method = stack_addmin; break;
 	default: retval = -100; goto done;
 	}
 	t0 = now_s();	/* same bracket as stacking.c:1918 -> :2102-2103 */
@@ -494,6 +502,7 @@ int oref_run(const oref_config *cfg, unsigned short *out, uint64_t irej[6],
 
 	if (!retval && gfit.data && out)
 		memcpy(out, gfit.data, npix * sizeof(WORD));
+	last_hi = retval ? -1 : (int) gfit.hi;
 	if (irej)
 		for (i = 0; i < 6; i++)
 			irej[i] = feed.irej[i / 2][i % 2];

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libsiril_ref.so")
 
-SUM, MEAN, MEDIAN, NORM_ONLY = 0, 1, 2, 3
+SUM, MEAN, MEDIAN, NORM_ONLY, ADDMAX, ADDMIN = 0, 1, 2, 3, 4, 5
 # reference enums (stacking.h:14-30)
 NO_REJEC, PERCENTILE, SIGMA, SIGMEDIAN, WINSORIZED, LINEARFIT = range(6)
 NO_NORM, ADDITIVE, MULTIPLICATIVE, ADDITIVE_SCALING, MULTIPLICATIVE_SCALING = range(5)
@@ -69,6 +69,7 @@ def lib():
                                           C.POINTER(C.c_double), C.POINTER(C.c_double),
                                           C.POINTER(C.c_double), C.POINTER(C.c_long)]
         _lib.oref_num_procs.restype = C.c_int
+        _lib.oref_last_hi.restype = C.c_int
     return _lib
 
 
@@ -98,7 +99,7 @@ def run(frames, method, rejection=NO_REJEC, normalize=NO_NORM, sig=(0.0, 0.0),
                             None if coeff is None else coeff.ctypes.data, timing.ctypes.data)
     if coeff is not None and normalize == NO_NORM:
         coeff[0], coeff[1], coeff[2] = 0.0, 1.0, 1.0     # compute_normalization's defaults (stacking.c:130-134)
-    return dict(out=out, irej=irej.reshape(3, 2), coeff=coeff, retval=rv,
+    return dict(out=out, irej=irej.reshape(3, 2), coeff=coeff, retval=rv, hi=lib().oref_last_hi(),
                 t_method=float(timing[0]), t_norm=float(timing[1]))
 
 

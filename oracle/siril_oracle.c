@@ -414,6 +414,48 @@ int so_stack_sum(const so_stack_args *a, uint16_t *out, uint64_t *maxim_out) {
 	return 0;
 }
 
+/* stack_addmax / stack_addmin: the brightest / darkest sample per pixel over the frames, with the
+ * registration shifts and the "ii > 0" test of stack_summing (stacking.c:918-936, 1074-1092).
+ * Pixels no frame reaches keep the initial value: 0 (calloc, :882) or 0xFFFF (memset, :1037-1038). */
+int so_stack_extreme(const so_stack_args *a, int take_max, uint16_t *out, uint16_t *extreme_out) {
+	const int W = a->width, H = a->height, C = a->channels, N = a->n_frames;
+	const size_t plane = (size_t) W * H;
+	uint16_t extreme = take_max ? 0 : 0xFFFF;
+	int j, layer, x, y;
+	size_t i;
+	if (N <= 1)
+		return -1;
+	for (i = 0; i < plane * C; i++)
+		out[i] = take_max ? 0 : 0xFFFF;
+	for (j = 0; j < N; j++) {
+		int sx = a->shiftx ? a->shiftx[j] : 0, sy = a->shifty ? a->shifty[j] : 0;
+		for (layer = 0; layer < C; layer++) {
+			const uint16_t *src = plane_of(a, j, layer);
+			uint16_t *dst = out + layer * plane;
+			for (y = 0; y < H; y++) {
+				int ny = y - sy, srow;
+				if (ny < 0 || ny >= H)
+					continue;
+				srow = a->row_order ? H - 1 - ny : ny;
+				for (x = 0; x < W; x++) {
+					int nx = x - sx;
+					uint16_t v, *d = dst + (size_t) y * W + x;
+					if (nx < 0 || nx >= W || (ny == 0 && nx == 0))
+						continue;
+					v = src[(size_t) srow * W + nx];
+					if (take_max ? v > *d : v < *d)
+						*d = v;
+					if (take_max ? *d > extreme : *d < extreme)
+						extreme = *d;
+				}
+			}
+		}
+	}
+	if (extreme_out)
+		*extreme_out = extreme;
+	return 0;
+}
+
 /* normalization of one sample on the median path, stacking.c:750-764: always
  * through double, NO_NORM included */
 static uint16_t normalize_median_path(uint16_t p, int mode, double offset, double mul, double scale) {

@@ -51,6 +51,9 @@ uint16_t so_round_to_word(double x);
 
 /* stack_summing, stacking.c:196-355.  maxim = the global maximum sum. */
 int so_stack_sum(const so_stack_args *a, uint16_t *out, uint64_t *maxim);
+/* stack_addmax (take_max != 0, stacking.c:824-972) / stack_addmin (stacking.c:979-1128).
+ * extreme = the value the reference stores in gfit.hi. */
+int so_stack_extreme(const so_stack_args *a, int take_max, uint16_t *out, uint16_t *extreme);
 /* stack_median, stacking.c:362-816 (hot loop :746-769) */
 int so_stack_median(const so_stack_args *a, uint16_t *out);
 /* stack_mean_with_rejection, stacking.c:1189-1858 (hot loop :1620-1802).

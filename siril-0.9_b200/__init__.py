@@ -9,6 +9,7 @@ usable.
 Operator layer (reference: src/stacking/stacking.c):
     seq = Sequence(frames_u16[N, C, H, W])
     stack_summing(seq)                      # stack_summing            :196
+    stack_addmax(seq) / stack_addmin(seq)   # stack_addmax :824 / stack_addmin :979
     stack_median(seq, normalize=...)        # stack_median             :362
     stack_mean_with_rejection(seq, ...)     # stack_mean_with_rejection :1189
     compute_normalization(seq, mode)        # compute_normalization    :125
@@ -122,10 +123,10 @@ class Callbacks(C.Structure):
 # every symbol include/siril_stack_cuda.h declares
 EXPORTS = [
     "ssc_bind_sequence", "ssc_unbind_sequence", "ssc_set_callbacks", "ssc_take_result", "ssc_release_workspace",
-    "ssc_stack_summing", "ssc_stack_median", "ssc_stack_mean_with_rejection",
+    "ssc_stack_summing", "ssc_stack_median", "ssc_stack_mean_with_rejection", "ssc_stack_addmax", "ssc_stack_addmin",
     "ssc_compute_normalization", "ssc_set_devices", "ssc_device_count", "ssc_set_kernel_path", "ssc_last_error",
     "ssc_version", "ssc_dev_stack_median", "ssc_dev_stack_mean", "ssc_dev_sum_accumulate",
-    "ssc_dev_sum_finish", "ssc_dev_histogram", "ssc_dev_ikss", "ssc_dev_norm_coeffs",
+    "ssc_dev_sum_finish", "ssc_dev_stack_extreme", "ssc_dev_histogram", "ssc_dev_ikss", "ssc_dev_norm_coeffs",
     "ssc_dev_synth_frames",
 ]
 
@@ -136,7 +137,8 @@ _lib.ssc_unbind_sequence.argtypes = [C.c_void_p]
 _lib.ssc_set_callbacks.argtypes = [C.POINTER(Callbacks)]
 _lib.ssc_set_callbacks.restype = None
 _lib.ssc_take_result.argtypes = [C.POINTER(Result)]
-for _n in ("ssc_stack_summing", "ssc_stack_median", "ssc_stack_mean_with_rejection"):
+for _n in ("ssc_stack_summing", "ssc_stack_median", "ssc_stack_mean_with_rejection", "ssc_stack_addmax",
+           "ssc_stack_addmin"):
     getattr(_lib, _n).argtypes = [C.POINTER(StackingArgs)]
 _lib.ssc_compute_normalization.argtypes = [C.POINTER(StackingArgs), C.POINTER(NormCoeff), C.c_int]
 _lib.ssc_set_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
@@ -146,6 +148,7 @@ _lib.ssc_dev_stack_mean.argtypes = [C.POINTER(Band), C.c_int, C.c_void_p, C.c_in
                                     C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
 _lib.ssc_dev_sum_accumulate.argtypes = [C.POINTER(Band), C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.ssc_dev_sum_finish.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+_lib.ssc_dev_stack_extreme.argtypes = [C.POINTER(Band), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.ssc_dev_histogram.argtypes = [C.POINTER(Band), C.c_void_p, C.c_void_p]
 _lib.ssc_dev_ikss.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.ssc_dev_norm_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -331,6 +334,22 @@ def stack_summing(seq, image_indices=None, filtering_criterion=None):
     return _take()
 
 
+def stack_addmax(seq, image_indices=None, filtering_criterion=None):
+    args = make_args(seq, image_indices, filtering_criterion=filtering_criterion)
+    rc = _lib.ssc_stack_addmax(C.byref(args))
+    if rc:
+        raise StackError(rc, "ssc_stack_addmax")
+    return _take()
+
+
+def stack_addmin(seq, image_indices=None, filtering_criterion=None):
+    args = make_args(seq, image_indices, filtering_criterion=filtering_criterion)
+    rc = _lib.ssc_stack_addmin(C.byref(args))
+    if rc:
+        raise StackError(rc, "ssc_stack_addmin")
+    return _take()
+
+
 def stack_median(seq, normalize=NO_NORM, image_indices=None, want_coeff=False):
     coeff = compute_normalization(seq, normalize, image_indices) if (want_coeff and normalize) else None
     args = make_args(seq, image_indices, normalize=normalize)
@@ -389,6 +408,11 @@ class dev:
     @staticmethod
     def sum_accumulate(band, acc_ptr, maxim_ptr, stream=0):
         dev._check(_lib.ssc_dev_sum_accumulate(C.byref(band), acc_ptr, maxim_ptr, stream), "ssc_dev_sum_accumulate")
+
+    @staticmethod
+    def stack_extreme(band, take_max, out_ptr, extreme_ptr, stream=0):
+        dev._check(_lib.ssc_dev_stack_extreme(C.byref(band), int(bool(take_max)), out_ptr, extreme_ptr, stream),
+                   "ssc_dev_stack_extreme")
 
     @staticmethod
     def sum_finish(acc_ptr, count, maxim_ptr, out_ptr, stream=0):

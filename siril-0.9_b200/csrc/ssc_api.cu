@@ -153,6 +153,15 @@ int ssc_dev_sum_finish(const uint32_t *acc, size_t count, const unsigned long lo
 	return SSC_OK;
 }
 
+int ssc_dev_stack_extreme(const ssc_band *band, int take_max, WORD *out, unsigned int *extreme, void *stream) {
+	int rc = check_band(band);
+	if (rc) return rc;
+	if (!out || !extreme) return fail(SSC_ERR_ARG, "null output");
+	rc = ssc::launch_extreme(*band, take_max != 0, out, extreme, (cudaStream_t) stream);
+	if (rc) return fail(rc, "addmax/addmin launch failed");
+	return SSC_OK;
+}
+
 int ssc_dev_histogram(const ssc_band *band, uint32_t *hist, void *stream) {
 	int rc = check_band(band);
 	if (rc) return rc;
@@ -243,7 +252,9 @@ int ssc_take_result(ssc_result *out) {
 // ---------------------------------------------------------------------------
 namespace {
 
-enum OpKind { OP_SUM, OP_MEDIAN, OP_MEAN };
+enum OpKind { OP_SUM, OP_MEDIAN, OP_MEAN, OP_ADDMAX, OP_ADDMIN };
+// the whole-frame operators (stack_summing, stack_addmax, stack_addmin) share geometry and frame selection
+inline bool frame_walker(OpKind op) { return op == OP_SUM || op == OP_ADDMAX || op == OP_ADDMIN; }
 
 struct Job {
 	OpKind op;
@@ -312,7 +323,7 @@ void source_rows(const Job &job, const Piece &pc, int H, int &buf_row0, int &buf
 		}
 	int lo, hi;	// [lo, hi) storage rows
 	const bool ser = job.seq->view.row_order == SSC_ROWS_SER;
-	if (job.op == OP_SUM) {
+	if (frame_walker(job.op)) {
 		// fits row y reads fits row y - sy; fits row = storage row (FITS) or H-1-row (SER)
 		int flo = pc.row0 - max_sy, fhi = pc.row0 + pc.rows - min_sy;
 		if (ser) { lo = H - fhi; hi = H - flo; } else { lo = flo; hi = fhi; }
@@ -427,6 +438,13 @@ int run_job(const Job &job) {
 			SSC_ENSURE(maxim, sizeof(unsigned long long));
 			d.acc = (uint32_t *) dc.acc.p; d.maxim = (unsigned long long *) dc.maxim.p;
 			CU(cudaMemsetAsync(d.maxim, 0, sizeof(unsigned long long), d.stream));
+		}
+		if (job.op == OP_ADDMAX || job.op == OP_ADDMIN) {
+			SSC_ENSURE(maxim, sizeof(unsigned long long));
+			d.maxim = (unsigned long long *) dc.maxim.p;
+			const unsigned long long neutral = job.op == OP_ADDMAX ? 0ull : 0xFFFFull;	// low word = the kernel's unsigned int
+			CU(cudaMemcpyAsync(d.maxim, &neutral, sizeof(neutral), cudaMemcpyHostToDevice, d.stream));
+			CU(cudaStreamSynchronize(d.stream));
 		}
 		if (need_norm) {
 			SSC_ENSURE(hist, (size_t) N * SSC_HIST_STRIDE * sizeof(uint32_t));
@@ -589,6 +607,9 @@ int run_job(const Job &job) {
 						}
 						if ((rc = ssc::launch_sum_finish(d.acc, (size_t) C * pc.rows * W, d.maxim, d.out, d.stream))) return fail(rc, "sum finish failed");
 					}
+				} else if (job.op == OP_ADDMAX || job.op == OP_ADDMIN) {
+					if ((rc = ssc::launch_extreme(bands[g], job.op == OP_ADDMAX, d.out, reinterpret_cast<unsigned int *>(d.maxim), d.stream)))
+						return fail(rc, "addmax/addmin launch failed");
 				} else {
 					if ((rc = ssc::launch_stack(p, job.op == OP_MEDIAN, d.stream)))
 						return fail(rc, "stack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -678,6 +699,16 @@ int run_job(const Job &job) {
 	for (int idx : job.images)
 		if (!job.seq->exposure.empty()) res.exposure += job.seq->exposure[idx];
 	if (job.op == OP_SUM) res.hi = h_max > 65535ull ? 65535 : (WORD) h_max;	// round_to_WORD(maxim), :324
+	if (job.op == OP_ADDMAX || job.op == OP_ADDMIN) {	// gfit.hi = round_to_WORD(maxim / minim), :947, :1103
+		unsigned int e = job.op == OP_ADDMAX ? 0u : 0xFFFFu;
+		for (auto &d : devs) {
+			unsigned long long m = 0;
+			CU(cudaSetDevice(d.id));
+			CU(cudaMemcpy(&m, d.maxim, sizeof(m), cudaMemcpyDeviceToHost));
+			e = job.op == OP_ADDMAX ? std::max(e, (unsigned int) m) : std::min(e, (unsigned int) m);
+		}
+		res.hi = (WORD) e;
+	}
 	res.t_h2d_ms = t_h2d;
 	res.t_device_ms = t_dev;
 	res.t_d2h_ms = t_d2h;
@@ -708,8 +739,8 @@ int make_job(struct stacking_args *args, OpKind op, Job &job) {
 	}
 	job.op = op;
 	const int number = job.seq->view.number;
-	if (op == OP_SUM) {
-		// stack_summing walks the whole sequence through the filter (stacking.c:223-231)
+	if (frame_walker(op)) {
+		// stack_summing / addmax / addmin walk the whole sequence through the filter (stacking.c:223-231, 855-863)
 		if (args->nb_images_to_stack <= 1) {
 			log_msg("No frame selected for stacking (select at least 2). Aborting.\n");
 			return fail(SSC_ERR_GENERIC, "fewer than 2 frames");
@@ -777,6 +808,20 @@ int ssc_release_workspace(void) {
 int ssc_stack_summing(struct stacking_args *args) {
 	Job job;
 	int rc = make_job(args, OP_SUM, job);
+	if (!rc) rc = run_job(job);
+	return finish(args, rc, "Stacking failed. Check the log.");
+}
+
+int ssc_stack_addmax(struct stacking_args *args) {
+	Job job;
+	int rc = make_job(args, OP_ADDMAX, job);
+	if (!rc) rc = run_job(job);
+	return finish(args, rc, "Stacking failed. Check the log.");
+}
+
+int ssc_stack_addmin(struct stacking_args *args) {
+	Job job;
+	int rc = make_job(args, OP_ADDMIN, job);
 	if (!rc) rc = run_job(job);
 	return finish(args, rc, "Stacking failed. Check the log.");
 }

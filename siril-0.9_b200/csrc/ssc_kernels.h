@@ -35,6 +35,7 @@ int launch_stack(const StackParams &p, int is_median, cudaStream_t stream);
 extern int g_kernel_path;	// 0 automatic, 1 general kernel only, 2 warp-specialised pipeline where eligible (ssc_set_kernel_path)
 
 // ssc_sum.cu
+int launch_extreme(const ssc_band &b, bool take_max, WORD *out, unsigned int *extreme, cudaStream_t stream);
 int launch_sum_accumulate(const ssc_band &b, uint32_t *acc, unsigned long long *maxim, cudaStream_t stream);
 int launch_sum_finish(const uint32_t *acc, size_t count, const unsigned long long *maxim, WORD *out,
 		cudaStream_t stream);

@@ -91,7 +91,8 @@ def test_no_cpu_fallback(pkg):
         pytest.skip("a CUDA device is present")
     frames = np.zeros((3, 1, 8, 8), np.uint16)
     seq = pkg.Sequence(frames)
-    for fn in (pkg.stack_summing, pkg.stack_median, pkg.stack_mean_with_rejection):
+    for fn in (pkg.stack_summing, pkg.stack_median, pkg.stack_mean_with_rejection, pkg.stack_addmax,
+               pkg.stack_addmin):
         with pytest.raises(pkg.StackError) as e:
             fn(seq)
         assert e.value.code == pkg.ERR_CUDA
@@ -104,6 +105,8 @@ def test_argument_errors_keep_reference_codes(pkg):
     assert pkg.lib().ssc_stack_median(C.byref(args)) == -1
     assert pkg.lib().ssc_stack_mean_with_rejection(C.byref(args)) == -1
     assert pkg.lib().ssc_stack_summing(C.byref(args)) == -1
+    assert pkg.lib().ssc_stack_addmax(C.byref(args)) == -1
+    assert pkg.lib().ssc_stack_addmin(C.byref(args)) == -1
     assert args.retval == -1
     args = pkg.make_args(seq)
     args.seq = 0xdead0                                      # never bound

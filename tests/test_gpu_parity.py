@@ -92,6 +92,41 @@ def test_sum_filter_callback(gpu, port):
     assert np.array_equal(res.data, port.stack_sum(fr[keep])["out"])
 
 
+# --------------------------------------------------------------------------- addmax / addmin
+@pytest.mark.parametrize("take_max", [True, False])
+@pytest.mark.parametrize("c,w", [(1, 32), (3, 24), (1, 21)])
+def test_addmax_addmin_bit_exact(gpu, port, take_max, c, w):
+    """stack_addmax / stack_addmin (stacking.c:824-1128): vector path (w % 8 == 0) and general path."""
+    fr = synth.make_random(9, c, 16, w, seed=31, hi=65536)
+    fr[:, :, 0, 0] = 65535 if take_max else 0               # source index 0 is never taken
+    op = gpu.stack_addmax if take_max else gpu.stack_addmin
+    res = op(gpu.Sequence(fr))
+    p = port.stack_extreme(fr, take_max)
+    assert np.array_equal(res.data, p["out"])
+    assert (res.data.reshape(c, -1)[:, 0] == (0 if take_max else 65535)).all()
+    assert res.hi == p["hi"]
+    sx = [0, 2, -3, 1, 0, -1, 5, 0, -20]
+    sy = [0, -2, 1, 3, -1, 0, -4, 17, 0]                     # one frame shifted out of the image entirely
+    for ro in (0, 1):
+        res = op(gpu.Sequence(fr, shiftx=sx, shifty=sy, row_order=ro))
+        p = port.stack_extreme(fr, take_max, shiftx=sx, shifty=sy, row_order=ro)
+        assert np.array_equal(res.data, p["out"]), ro
+        assert res.hi == p["hi"]
+        res = op(gpu.Sequence(fr, row_order=ro))
+        assert np.array_equal(res.data, port.stack_extreme(fr, take_max, row_order=ro)["out"]), ro
+
+
+def test_addmax_filter_and_errors(gpu, port):
+    fr = synth.make_random(8, 1, 8, 16, seed=6, hi=500)
+    keep = [0, 2, 3, 6]
+    crit = gpu.FILTER_FN(lambda seq, i, p: int(i in keep))
+    res = gpu.stack_addmax(gpu.Sequence(fr), filtering_criterion=crit)
+    assert np.array_equal(res.data, port.stack_extreme(fr[keep], True)["out"])
+    with pytest.raises(gpu.StackError) as e:
+        gpu.stack_addmin(gpu.Sequence(fr), image_indices=[0])
+    assert e.value.code == -1                                # "No frame selected for stacking (select at least 2)"
+
+
 # --------------------------------------------------------------------------- mean with rejection
 @pytest.mark.parametrize("rej", list(REJ))
 @pytest.mark.parametrize("norm", [0, 1, 2, 3, 4])
@@ -215,6 +250,11 @@ def test_golden_fixtures(gpu):
             assert np.array_equal(res.data, g["out"]), f
         elif kind == "sum":
             assert np.array_equal(gpu.stack_summing(seq).data, g["out"]), f
+        elif kind in ("addmax", "addmin"):
+            seq = gpu.Sequence(fr, shiftx=g["shiftx"], shifty=g["shifty"])
+            res = (gpu.stack_addmax if kind == "addmax" else gpu.stack_addmin)(seq)
+            assert np.array_equal(res.data, g["out"]), f
+            assert res.hi == int(g["hi"]), f
         else:
             rj = int(g["rejection"])
             res = gpu.stack_mean_with_rejection(seq, rj, tuple(g["sig"]), int(g["normalize"]))

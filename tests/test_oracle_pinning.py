@@ -71,6 +71,28 @@ def test_sum_with_shifts_matches_reference(port, refrun):
         assert np.array_equal(r["out"], p["out"]), ro
 
 
+@pytest.mark.parametrize("take_max", [True, False])
+@pytest.mark.parametrize("c", [1, 3])
+def test_addmax_addmin_match_reference(port, refrun, take_max, c):
+    """stack_addmax / stack_addmin (stacking.c:824-1128): image and gfit.hi, with and without
+    registration shifts, both row conventions; source index 0 is never taken."""
+    fr = synth.make_random(7, c, 18, 26, seed=21 + c, hi=65536)
+    fr[:, :, 0, 0] = 65535 if take_max else 0               # would win if index 0 were read
+    meth = refrun.ADDMAX if take_max else refrun.ADDMIN
+    sx = [0, 2, -3, 1, 0, -1, 5]
+    sy = [0, -2, 1, 3, -1, 0, -4]
+    for ro in (0, 1):
+        for shx, shy in ((None, None), (sx, sy), (sx, None)):
+            r = refrun.run(fr, meth, shiftx=shx, shifty=shy, row_order=ro)
+            p = port.stack_extreme(fr, take_max, shiftx=shx, shifty=shy, row_order=ro)
+            assert r["retval"] == 0 and p["retval"] == 0
+            assert np.array_equal(r["out"], p["out"]), (ro, shx)
+            assert r["hi"] == p["hi"], (ro, shx)
+    p = port.stack_extreme(fr, take_max)
+    assert (p["out"].reshape(c, -1)[:, 0] == (0 if take_max else 65535)).all()   # never touched: calloc / memset 0xFF
+    assert port.stack_extreme(fr[:1], take_max)["retval"] == -1                  # "select at least 2"
+
+
 @pytest.mark.parametrize("rej", list(REJ))
 @pytest.mark.parametrize("norm", [0, 1, 2, 3, 4])
 def test_mean_matches_reference(port, refrun, rej, norm):
@@ -178,6 +200,10 @@ def test_golden_vectors(port):
             out = port.stack_median(fr, normalize=int(g["normalize"]), coeff=g["coeff"])["out"]
         elif kind == "sum":
             out = port.stack_sum(fr)["out"]
+        elif kind in ("addmax", "addmin"):
+            r = port.stack_extreme(fr, kind == "addmax", shiftx=g["shiftx"], shifty=g["shifty"])
+            out = r["out"]
+            assert r["hi"] == int(g["hi"]), f
         else:
             r = port.stack_mean(fr, int(g["rejection"]), tuple(g["sig"]), int(g["normalize"]), coeff=g["coeff"])
             out = r["out"]
