@@ -17,7 +17,22 @@ struct LeftoverList {
 	unsigned int capacity;
 	uint4 *cols;			// [capacity][NP * 2 bytes]: the sorted column of each item, contiguous
 	uint2 *meta;			// [capacity]: result element index, layer
+	unsigned int *ids;		// or (ssc_stack_fast.cu): [capacity] indices of pixels for the general kernel's list mode
 };
+
+// append one pixel index per flagged lane: one atomic per warp
+__device__ __forceinline__ void leftover_push(const LeftoverList &list, bool flagged, unsigned int pixel, int lane) {
+	const unsigned int mask = __ballot_sync(0xffffffffu, flagged);
+	if (mask == 0) return;
+	const int leader = __ffs(mask) - 1;
+	unsigned int base = 0;
+	if (lane == leader) base = atomicAdd(list.count, (unsigned int) __popc(mask));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	if (flagged) {
+		const unsigned int slot = base + __popc(mask & ((1u << lane) - 1));
+		if (slot < list.capacity) list.ids[slot] = pixel;	// capacity = every pixel of the launch: always true
+	}
+}
 
 // The leftover list, one pixel per thread: the column is already sorted, the sums are rebuilt.
 template <int NP>
@@ -104,6 +119,37 @@ inline int leftover_list(int np, unsigned long long pixels, LeftoverList &list, 
 	list.capacity = (unsigned int) st.capacity;
 	list.cols = (uint4 *) st.cols;
 	list.meta = (uint2 *) st.meta;
+	list.ids = nullptr;
+	return SSC_OK;
+}
+
+// Index-only list for the register kernel (ssc_stack_fast.cu): room for every pixel of the launch,
+// 4 bytes each, so nothing ever has to be finished in place.
+struct LeftoverIdStore {
+	unsigned int *count = nullptr, *ids = nullptr;
+	size_t capacity = 0;
+};
+inline LeftoverIdStore g_leftover_id_store[64];
+
+inline int leftover_ids(unsigned long long pixels, LeftoverList &list, cudaStream_t stream) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64 || pixels > 0xFFFFFFF0ull) return SSC_ERR_ARG;
+	LeftoverIdStore &st = g_leftover_id_store[dev];
+	if (!st.count && cudaMalloc(&st.count, sizeof(unsigned int)) != cudaSuccess) return SSC_ERR_CUDA;
+	if (st.capacity < pixels) {
+		if (st.ids) cudaFree(st.ids);
+		st.ids = nullptr;
+		st.capacity = 0;
+		if (cudaMalloc(&st.ids, (size_t) pixels * sizeof(unsigned int)) != cudaSuccess) return SSC_ERR_CUDA;
+		st.capacity = (size_t) pixels;
+	}
+	if (cudaMemsetAsync(st.count, 0, sizeof(unsigned int), stream) != cudaSuccess) return SSC_ERR_CUDA;
+	list.count = st.count;
+	list.capacity = (unsigned int) pixels;
+	list.cols = nullptr;
+	list.meta = nullptr;
+	list.ids = st.ids;
 	return SSC_OK;
 }
 

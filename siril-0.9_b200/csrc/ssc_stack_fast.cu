@@ -48,13 +48,64 @@ __device__ __forceinline__ void normalize_all(unsigned int (&v)[NP], int N, cons
 #endif
 enum { MODE_MEDIAN = 0, MODE_NOREJ = 1, MODE_SIGMA_REG = 2, MODE_QUEUE = 3 };
 
+// MODE_SIGMA_REG stages the band through shared memory so that everything before the sorting
+// network is ROLLED code: the straight-line part of a tile then stays under the 32 KB of
+// instructions an SM serves at full rate (tools/micro/ifetch.cu: beyond that, issue drops to
+// ~0.3-0.6 warp-instructions per clock and scheduler whatever the pipes could do).
+// One thread's staging column: stage[f * FAST_THREADS + tid], conflict-free.
+template <int NP, int KIND>
+__device__ __forceinline__ void normalize_staged(unsigned int *stage_t, int stride, const double *s_coef,
+		unsigned int &Sa, unsigned int &Sb, unsigned long long &Qa, unsigned long long &Qb) {
+#pragma unroll 4
+	for (int f = 0; f < NP; f++) {
+		unsigned int w = stage_t[f * stride];
+		if constexpr (KIND != NO_NORM) {
+			double off = 0.0, mul = 1.0, sc = 1.0;
+			if constexpr (KIND == ADDITIVE || KIND == ADDITIVE_SCALING) off = s_coef[f];
+			if constexpr (KIND == MULTIPLICATIVE || KIND == MULTIPLICATIVE_SCALING) mul = s_coef[64 + f];
+			if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) sc = s_coef[128 + f];
+			w = normalize_pair_fast<KIND>(w, off, mul, sc, Qa, Qb);
+			stage_t[f * stride] = w;
+		} else {
+			const unsigned int pa = w & 0xFFFFu, pb = w >> 16;
+			Qa += (unsigned long long) pa * pa;
+			Qb += (unsigned long long) pb * pb;
+		}
+		Sa = __dp2a_lo(w, 0x0001u, Sa);		// IDP.2A: acc + lo16 * 1 + hi16 * 0
+		Sb = __dp2a_lo(w, 0x0100u, Sb);
+	}
+}
+
+// True when the first sigma-clipping pass (stacking.c:1674-1690) provably rejects nothing in a
+// full stack of NP samples.  The exact test is  d_lo > floor(X_lo)  /  d_hi > floor(X_hi)  with
+// X = 2 * sig * sigma in FP64 (see the queue pass below) and d_lo = M2 - 2 min, d_hi = 2 max - M2
+// (M2 = twice the median; if the extremes stay, everything stays).  Here X is estimated in FP32
+// from the exact integer D = n Q - S^2 (< 2^44): conversion, two products, an approximate square
+// root and the product with the parameter are each good to ~1e-7 relative, so t * (1 - 1e-4) is
+// below X, and  d < t (1 - 1e-4) - 1  implies  d < X - 1 < floor(X).  d is an integer below 2^24,
+// exact in FP32.  Anything not provably clear is evaluated exactly.
+template <int NP>
+__device__ __forceinline__ bool clip_cannot_fire(unsigned long long S, unsigned long long Q, int d_lo, int d_hi,
+		float sig_low_f, float sig_high_f) {
+	const unsigned long long D = (unsigned long long) NP * Q - S * S;
+	float sigma;
+	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sigma) : "f"(__ull2float_rn(D) * (1.0f / ((float) NP * (float) (NP - 1)))));
+	const float t_lo = 2.0f * sig_low_f * sigma * 0.9999f - 1.0f, t_hi = 2.0f * sig_high_f * sigma * 0.9999f - 1.0f;
+	return (d_lo == 0 || (float) d_lo < t_lo) && (d_hi == 0 || (float) d_hi < t_hi);
+}
+
+constexpr int FAST_QUEUE_WORDS = 12, FAST_QUEUE_CAP = 96;	// per warp: < 32 waiting + up to 64 new per tile
+
 // FULL: n_frames == NP (no sentinel padding, no per-frame bound checks in the unrolled code)
 // MODE: which tail follows the network (one per instantiation: the kernel is instruction-fetch
 //       sensitive, dead alternatives are not carried along)
-constexpr int FAST_THREADS = 128;
+#ifndef SSC_FAST_THREADS
+#define SSC_FAST_THREADS 128
+#endif
+constexpr int FAST_THREADS = SSC_FAST_THREADS;
 
 template <int NP, bool FULL, int MODE>
-__global__ void __launch_bounds__(FAST_THREADS, 4)
+__global__ void __launch_bounds__(FAST_THREADS, 512 / FAST_THREADS)
 k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	extern __shared__ unsigned int cols[];		// [NP][FAST_THREADS] packed columns
 	__shared__ double s_coef[3 * 64];
@@ -67,10 +118,18 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	__shared__ unsigned int s_S[2 * FAST_THREADS];
 	__shared__ unsigned long long s_Q[2 * FAST_THREADS];
 
+
 	const ssc_band &b = p.band;
-	const int W = b.width, N = FULL ? NP : b.n_frames, tid = threadIdx.x;
+	const int W = b.width, N = FULL ? NP : b.n_frames, tid = threadIdx.x, lane = tid & 31;
 	const int W2 = W >> 1;
 	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
+	// MODE_SIGMA_REG: the dynamic shared memory holds the per-warp queues of pixels whose clipping
+	// has to be evaluated exactly, [warp][FAST_QUEUE_WORDS][FAST_QUEUE_CAP]
+	// behind the staging buffer [NP][FAST_THREADS] (see normalize_staged)
+	unsigned int (*queue)[FAST_QUEUE_CAP] = reinterpret_cast<unsigned int (*)[FAST_QUEUE_CAP]>(cols + NP * FAST_THREADS)
+			+ (tid >> 5) * FAST_QUEUE_WORDS;
+	int qcount = 0;		// items on this warp's queue (warp-uniform)
+	const float sig_low_f = (float) p.sig_low, sig_high_f = (float) p.sig_high;
 
 	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
 	if (tid == 0) s_fast_norm = 1;
@@ -96,13 +155,35 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * W2;
 	// Blocks loop over tiles (the launcher bounds the grid): the tables, the coefficient copy and
 	// their barriers above are paid once per block instead of once per tile.
-	for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+	// (MODE_SIGMA_REG runs one more round after its last tile, to drain the warp queues)
+	for (unsigned long long tile = blockIdx.x; ; tile += gridDim.x) {
+	const bool more = tile < n_tiles;
+	if (MODE != MODE_SIGMA_REG && !more) break;
+#ifdef SSC_TILE_SYNC
+	if (MODE == MODE_SIGMA_REG) __syncthreads();
+#endif
+	if (more) {
 	unsigned long long g = tile * FAST_THREADS + tid;
 	const bool active = g < total;
+	if constexpr (MODE == MODE_SIGMA_REG) {
+		if (norm && !s_fast_norm) {	// coefficients outside the fast normalization's domain (block-uniform):
+			leftover_push(list, active, (unsigned int) (2 * g), lane);		// every pixel goes to the
+			leftover_push(list, active, (unsigned int) (2 * g + 1), lane);	// general kernel
+			continue;
+		}
+	}
 	if (!active) g = total - 1;
-	const int x2 = (int) (g % W2);
-	const int rr = (int) ((g / W2) % b.out_rows);
-	const int layer = (int) (g / ((unsigned long long) W2 * b.out_rows));
+	int x2, rr, layer;
+	if constexpr (MODE == MODE_SIGMA_REG) {	// (the launcher guarantees 32-bit pixel counts: no 64-bit division)
+		const unsigned int g32 = (unsigned int) g, row = g32 / (unsigned int) W2;
+		x2 = (int) (g32 - row * (unsigned int) W2);
+		layer = (int) (row / (unsigned int) b.out_rows);
+		rr = (int) (row - (unsigned int) layer * (unsigned int) b.out_rows);
+	} else {
+		x2 = (int) (g % W2);
+		rr = (int) ((g / W2) % b.out_rows);
+		layer = (int) (g / ((unsigned long long) W2 * b.out_rows));
+	}
 	const int R = b.out_row0 + rr;				// result storage row (stacking.c:731,1600)
 	const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - R : R;
 	// per-thread offset inside a frame (32 bits: a frame holds < 2^32 pixel pairs) on top of a
@@ -112,10 +193,37 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	const unsigned int *frames32 = reinterpret_cast<const unsigned int *>(b.frames);
 	const size_t fstride2 = b.frame_stride >> 1;
 
-	// ---- gather: one packed load per frame, all issued before first use ----
 	unsigned int v[NP];
 	const char *ptr = reinterpret_cast<const char *>(frames32 + toff);
 	const size_t fstride_bytes = fstride2 * sizeof(unsigned int);
+	unsigned long long Qa = 0, Qb = 0;	// exact sums of squares of the (normalized) samples
+	unsigned int Sa = 0, Sb = 0;		// exact sums (fit 32 bits)
+	bool have_q = false;
+	if constexpr (MODE == MODE_SIGMA_REG) {
+		// ---- gather: one asynchronous 4-byte copy per frame straight into the thread's staging
+		// column (all in flight at once), then normalization and the sums in a rolled loop over it
+		unsigned int *stage_t = cols + tid;
+		unsigned int sdst = (unsigned int) __cvta_generic_to_shared(stage_t);
+#pragma unroll 4
+		for (int f = 0; f < NP; f++) {
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sdst), "l"(ptr) : "memory");
+			sdst += FAST_THREADS * sizeof(unsigned int);
+			ptr += fstride_bytes;
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		switch (norm ? p.normalize : NO_NORM) {
+		case NO_NORM: normalize_staged<NP, NO_NORM>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
+		case ADDITIVE: normalize_staged<NP, ADDITIVE>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
+		case MULTIPLICATIVE: normalize_staged<NP, MULTIPLICATIVE>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
+		case ADDITIVE_SCALING: normalize_staged<NP, ADDITIVE_SCALING>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
+		default: normalize_staged<NP, MULTIPLICATIVE_SCALING>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
+		}
+		have_q = true;
+#pragma unroll
+		for (int f = 0; f < NP; f++) v[f] = stage_t[f * FAST_THREADS];
+	} else {
+	// ---- gather: one packed load per frame, all issued before first use ----
 #pragma unroll
 	for (int f = 0; f < NP; f++) {
 		v[f] = (FULL || f < N) ? __ldg(reinterpret_cast<const unsigned int *>(ptr)) : 0xFFFFFFFFu;
@@ -123,8 +231,6 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	}
 
 	// ---- normalize (stacking.c:1635-1652; median path :750-764) ----
-	unsigned long long Qa = 0, Qb = 0;	// exact sums of squares of the (normalized) samples
-	bool have_q = false;
 	if (norm) {
 		if (s_fast_norm) {
 			have_q = true;
@@ -149,6 +255,7 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 			for (int f = 0; f < NP; f++) v[f] = cols[f * FAST_THREADS + tid];
 		}
 	}
+	}
 
 	unsigned int res[2];
 	WORD *dst = p.out + out_idx;
@@ -172,12 +279,13 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	} else {
 		// exact integer sums of the (normalized) samples; the sum fits 32 bits and comes straight
 		// from the packed words (IDP.2A: acc + lo16 * 1 + hi16 * 0), the sum of squares needs 64
-		unsigned int Sa = 0, Sb = 0;
+		if constexpr (MODE != MODE_SIGMA_REG) {		// (MODE_SIGMA_REG: summed in the rolled loop)
 #pragma unroll
-		for (int f = 0; f < NP; f++) {
-			if (FULL || f < N) {
-				Sa = __dp2a_lo(v[f], 0x0001u, Sa);
-				Sb = __dp2a_lo(v[f], 0x0100u, Sb);
+			for (int f = 0; f < NP; f++) {
+				if (FULL || f < N) {
+					Sa = __dp2a_lo(v[f], 0x0001u, Sa);
+					Sb = __dp2a_lo(v[f], 0x0100u, Sb);
+				}
 			}
 		}
 		if (!have_q && MODE != MODE_NOREJ) {
@@ -199,130 +307,58 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 			if (active) *reinterpret_cast<unsigned int *>(dst) = res[0] | (res[1] << 16);
 			continue;
 		} else if constexpr (MODE == MODE_SIGMA_REG) {
-			// ---- sigma clipping (stacking.c:1674-1695) entirely in registers.  In a sorted stack the
-			// low flags are a prefix and the high flags a suffix, the survivors stay [nl, NP - nh), and
-			// each pass only looks at the sums, the two middle survivors and the next candidates at
-			// both ends -- all of which sit at STATIC register indices as long as few samples go:
-			// candidates v[0..2] below, v[NP-1..NP-6] above, medians within v[NP/2-3..NP/2+1].  Both
-			// pixels of the pair run side by side.  Whoever needs more (a third low, a sixth high, a
-			// fifth pass) is handed to the leftover list.  With NP >= 32 and at most 7 rejections the
-			// reference's "N - r <= 4" break (:1684) cannot be reached here.
-			static_assert(FULL && NP >= 32, "register-resident clipping needs a full stack of >= 32 frames");
+			// ---- sigma clipping (stacking.c:1674-1695).  In a sorted stack the low flags are a prefix
+			// and the high flags a suffix, the survivors stay [nl, NP - nh), and each pass only looks at
+			// the sums, the two middle survivors and the next candidates at both ends: v[0..2] below,
+			// v[NP-1..NP-6] above, medians within v[NP/2-3..NP/2+1].
+			// Most pixels reject nothing, which a conservative single-precision test on the extreme
+			// samples proves without any FP64 work (see clip_cannot_fire).  The others are packed into
+			// 48-byte items -- the 14 candidates, the sums, the result address -- on the warp's queue
+			// and evaluated exactly, one pixel per lane with FULL warps, one pass per round (an item
+			// that rejected something goes back on the queue for its next pass).  Whoever leaves the
+			// candidate window (a third low, a sixth high) goes to the leftover list.  With NP >= 32
+			// and at most 7 rejections the reference's "N - r <= 4" break (:1684) cannot be reached.
+			static_assert(FULL && NP >= 32 && (NP & (NP - 1)) == 0, "needs a full stack of 32 or 64 frames");
 			sort_network<NP>(v);
-			int nl[2] = {0, 0}, nh[2] = {0, 0};
-			unsigned int rl[2] = {0, 0}, rh[2] = {0, 0};
-			bool done[2] = {false, false}, punt[2] = {false, false};
-#pragma unroll 1
-			for (int it = 0; it <= SSC_SIGMA_REG_PASSES; it++) {
-				if (it == SSC_SIGMA_REG_PASSES) {	// one more pass would be needed
-					punt[0] = !done[0];
-					punt[1] = !done[1];
-					break;
-				}
-#pragma unroll
-				for (int h = 0; h < 2; h++) {
-					if (done[h] || punt[h]) continue;
-					const int Nc = NP - nl[h] - nh[h];
-					const double sigma = sd_from_sums<true>(S[h], Q[h], Nc, &tables);
-					const int lhs = nl[h] + ((Nc - 1) >> 1), rhs = nl[h] + (Nc >> 1);
-					unsigned int ml = 0, mr = 0;
-#pragma unroll
-					for (int k = NP / 2 - 3; k <= NP / 2 + 1; k++) {
-						const unsigned int e = h ? v[k] >> 16 : v[k] & 0xFFFFu;
-						if (lhs == k) ml = e;
-						if (rhs == k) mr = e;
-					}
-					// sigma_clipping (:1152,1156) in integers: the median is M2 / 2 with M2 an integer and the
-					// sample e an integer, so (median - e) is exact in FP64 and
-					//   median - e > tl  <=>  M2 - 2e > 2 tl  <=>  M2 - 2e > floor(2 tl)      (tl >= 0)
-					// and likewise on the high side: one float-to-int conversion per pass and side instead
-					// of a conversion, a subtraction and a compare per candidate.
-					const int M2 = lhs == rhs ? 2 * (int) ml : (int) (ml + mr);
-					const int TL = __double2int_rd(fmin(dmul(2.0, dmul(p.sig_low, sigma)), 1073741824.0));
-					const int TH = __double2int_rd(fmin(dmul(2.0, dmul(p.sig_high, sigma)), 1073741824.0));
-					int n = 0;
-#pragma unroll
-					for (int k = 0; k < 3; k++) {		// low candidates, in scan order
-						const unsigned int e = h ? v[k] >> 16 : v[k] & 0xFFFFu;
-						if (nl[h] == k && M2 - 2 * (int) e > TL) {
-							nl[h]++; n++; rl[h]++;
-							S[h] -= e; Q[h] -= (unsigned long long) e * e;
-						}
-					}
-#pragma unroll
-					for (int k = 0; k < 6; k++) {		// high candidates, from the top
-						const unsigned int e = h ? v[NP - 1 - k] >> 16 : v[NP - 1 - k] & 0xFFFFu;
-						if (nh[h] == k && 2 * (int) e - M2 > TH) {
-							nh[h]++; n++; rh[h]++;
-							S[h] -= e; Q[h] -= (unsigned long long) e * e;
-						}
-					}
-					if (nl[h] == 3 || nh[h] == 6) punt[h] = true;	// the next candidate is out of the window
-					else if (n == 0) done[h] = true;		// do { } while (n > 0 && N > 3)
-				}
-				if ((done[0] || punt[0]) && (done[1] || punt[1])) break;
-			}
+			bool need[2];
 #pragma unroll
 			for (int h = 0; h < 2; h++) {
-				res[h] = mean_to_word<true>(S[h], NP - nl[h] - nh[h], &tables);
-				punt[h] = punt[h] && active;
+				const unsigned int lo = h ? v[0] >> 16 : v[0] & 0xFFFFu, hi = h ? v[NP - 1] >> 16 : v[NP - 1] & 0xFFFFu;
+				const unsigned int ml = h ? v[NP / 2 - 1] >> 16 : v[NP / 2 - 1] & 0xFFFFu;
+				const unsigned int mr = h ? v[NP / 2] >> 16 : v[NP / 2] & 0xFFFFu;
+				const int M2 = (int) (ml + mr);
+				need[h] = active && !clip_cannot_fire<NP>(S[h], Q[h], M2 - 2 * (int) lo, 2 * (int) hi - M2, sig_low_f, sig_high_f);
+				res[h] = (unsigned int) ((S[h] + NP / 2) / NP);	// round_to_WORD(S / NP), NP a power of two
 			}
-			// ---- finished pixels: results and counters ----
 			if (active) {
-				if (!punt[0] && !punt[1]) {
+				if (!need[0] && !need[1]) {
 					*reinterpret_cast<unsigned int *>(dst) = res[0] | (res[1] << 16);
 				} else {
-					if (!punt[0]) dst[0] = (WORD) res[0];
-					if (!punt[1]) dst[1] = (WORD) res[1];
+					if (!need[0]) dst[0] = (WORD) res[0];
+					if (!need[1]) dst[1] = (WORD) res[1];
 				}
-				const unsigned int cl = (punt[0] ? 0 : rl[0]) + (punt[1] ? 0 : rl[1]);
-				const unsigned int ch = (punt[0] ? 0 : rh[0]) + (punt[1] ? 0 : rh[1]);
-				if (cl) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) cl);
-				if (ch) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) ch);
 			}
-			// ---- the others: to the leftover list (one atomic per warp), or in place if it is full ----
-			bool in_place = false;
 #pragma unroll
 			for (int h = 0; h < 2; h++) {
-				const unsigned int mask = __ballot_sync(0xffffffffu, punt[h]);
+				const unsigned int mask = __ballot_sync(0xffffffffu, need[h]);
 				if (mask == 0) continue;
-				const int lane = tid & 31;
-				unsigned int base = 0;
-				if (lane == __ffs(mask) - 1) base = atomicAdd(list.count, (unsigned int) __popc(mask));
-				base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
-				if (punt[h]) {
-					const unsigned int slot = base + __popc(mask & ((1u << lane) - 1));
-					if (slot < list.capacity) {
-						uint4 *d = list.cols + (size_t) slot * (NP / 8);
-#pragma unroll
-						for (int q = 0; q < NP / 8; q++) {
-							const unsigned int sel = h ? 0x7632u : 0x5410u;
-							d[q] = make_uint4(__byte_perm(v[8 * q], v[8 * q + 1], sel), __byte_perm(v[8 * q + 2], v[8 * q + 3], sel),
-									__byte_perm(v[8 * q + 4], v[8 * q + 5], sel), __byte_perm(v[8 * q + 6], v[8 * q + 7], sel));
-						}
-						list.meta[slot] = make_uint2(out_idx + h, (unsigned int) layer);
-						punt[h] = false;
-					} else {
-						in_place = true;
-					}
+				if (need[h]) {
+					const int slot = qcount + __popc(mask & ((1u << lane) - 1));
+					const unsigned int sel = h ? 0x7632u : 0x5410u;	// this pixel's halves of two registers
+					queue[0][slot] = __byte_perm(v[0], v[1], sel);
+					queue[1][slot] = __byte_perm(v[2], v[NP / 2 - 3], sel);
+					queue[2][slot] = __byte_perm(v[NP / 2 - 2], v[NP / 2 - 1], sel);
+					queue[3][slot] = __byte_perm(v[NP / 2], v[NP / 2 + 1], sel);
+					queue[4][slot] = __byte_perm(v[NP - 1], v[NP - 2], sel);
+					queue[5][slot] = __byte_perm(v[NP - 3], v[NP - 4], sel);
+					queue[6][slot] = __byte_perm(v[NP - 5], v[NP - 6], sel);
+					queue[7][slot] = (unsigned int) S[h];
+					queue[8][slot] = (unsigned int) Q[h];
+					queue[9][slot] = (unsigned int) (Q[h] >> 32);
+					queue[10][slot] = out_idx + h;
+					queue[11][slot] = (unsigned int) layer << 8;	// nl | nh << 4 | layer << 8
 				}
-			}
-			if (__syncthreads_or(in_place)) {	// list full (adversarial data): finish in place, slowly
-#pragma unroll
-				for (int f = 0; f < NP; f++) cols[f * FAST_THREADS + tid] = v[f];
-#pragma unroll 1
-				for (int h = 0; h < 2; h++) {
-					if (!punt[h]) continue;
-					Column c{reinterpret_cast<WORD *>(cols) + 2 * tid + h, 2 * FAST_THREADS};
-					unsigned long long s0 = 0, q0 = 0;
-					for (int f = 0; f < NP; f++) { const unsigned int e = c.get(f); s0 += e; q0 += sq(e); }
-					RejectState ist{0, 0, 0, 0};
-					dst[h] = (WORD) reject_sorted_and_mean<true>(c, NP, SIGMA, p.sig_low, p.sig_high, s0, q0, ist, &tables);
-					if (ist.rej_lo) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) ist.rej_lo);
-					if (ist.rej_hi) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) ist.rej_hi);
-					if (ist.guard) atomicAdd(&blk_counters[6], 1ull);
-					if (ist.cap) atomicAdd(&blk_counters[7], 1ull);
-				}
+				qcount += __popc(mask);
 			}
 		} else {	// MODE_QUEUE: every other rejection / stack size, through the block's work queue
 			sort_network<NP>(v);
@@ -398,7 +434,88 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 			if (active) *reinterpret_cast<unsigned int *>(dst) = res[0] | (res[1] << 16);
 		}
 	}
-	if (MODE == MODE_QUEUE || MODE == MODE_SIGMA_REG) __syncthreads();	// shared-memory columns / queue are reused by the next tile
+	if (MODE == MODE_QUEUE) __syncthreads();	// shared-memory columns / queue are reused by the next tile
+	}	// if (more)
+	if constexpr (MODE == MODE_SIGMA_REG) {
+		// ---- exact clipping passes on the warp's queue: full warps while tiles keep coming, whatever
+		// is left after the last one.  One pass of one pixel per lane and round.
+		const int min_fill = more ? 32 : 1;
+		while (qcount >= min_fill) {
+			const int cnt = qcount < 32 ? qcount : 32;
+			const int slot = qcount - cnt + lane;
+			const bool mine = lane < cnt;
+			unsigned int w[FAST_QUEUE_WORDS];
+#pragma unroll
+			for (int k = 0; k < FAST_QUEUE_WORDS; k++) w[k] = mine ? queue[k][slot] : 0u;
+			__syncwarp();
+			qcount -= cnt;
+			const unsigned int low[3] = {w[0] & 0xFFFFu, w[0] >> 16, w[1] & 0xFFFFu};
+			const unsigned int mid[5] = {w[1] >> 16, w[2] & 0xFFFFu, w[2] >> 16, w[3] & 0xFFFFu, w[3] >> 16};
+			const unsigned int high[6] = {w[4] & 0xFFFFu, w[4] >> 16, w[5] & 0xFFFFu, w[5] >> 16, w[6] & 0xFFFFu, w[6] >> 16};
+			unsigned long long S1 = w[7], Q1 = (unsigned long long) w[8] | ((unsigned long long) w[9] << 32);
+			int nl = (int) (w[11] & 15u), nh = (int) ((w[11] >> 4) & 15u);
+			const int item_layer = (int) (w[11] >> 8);
+			const int Nc = NP - nl - nh;
+			const double sigma = sd_from_sums<true>(S1, Q1, Nc, &tables);
+			const int lhs = nl + ((Nc - 1) >> 1) - (NP / 2 - 3), rhs = nl + (Nc >> 1) - (NP / 2 - 3);
+			unsigned int ml = 0, mr = 0;
+#pragma unroll
+			for (int k = 0; k < 5; k++) {
+				if (lhs == k) ml = mid[k];
+				if (rhs == k) mr = mid[k];
+			}
+			// sigma_clipping (:1152,1156) in integers: the median is M2 / 2 with M2 an integer and the
+			// sample e an integer, so (median - e) is exact in FP64 and
+			//   median - e > tl  <=>  M2 - 2e > 2 tl  <=>  M2 - 2e > floor(2 tl)      (tl >= 0)
+			// and likewise on the high side: one float-to-int conversion per pass and side instead
+			// of a conversion, a subtraction and a compare per candidate.
+			const int M2 = lhs == rhs ? 2 * (int) ml : (int) (ml + mr);
+			const int TL = __double2int_rd(fmin(dmul(2.0, dmul(p.sig_low, sigma)), 1073741824.0));
+			const int TH = __double2int_rd(fmin(dmul(2.0, dmul(p.sig_high, sigma)), 1073741824.0));
+			int n = 0;
+#pragma unroll
+			for (int k = 0; k < 3; k++) {		// low candidates, in scan order
+				const unsigned int e = low[k];
+				if (nl == k && M2 - 2 * (int) e > TL) {
+					nl++; n++;
+					S1 -= e; Q1 -= (unsigned long long) e * e;
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < 6; k++) {		// high candidates, from the top
+				const unsigned int e = high[k];
+				if (nh == k && 2 * (int) e - M2 > TH) {
+					nh++; n++;
+					S1 -= e; Q1 -= (unsigned long long) e * e;
+				}
+			}
+			const bool punt = mine && (nl == 3 || nh == 6);		// the next candidate is outside the window
+			const bool done = mine && !punt && n == 0;		// do { } while (n > 0 && N > 3)
+			const bool again = mine && !punt && !done;
+			if (done) {
+				p.out[w[10]] = (WORD) mean_to_word<true>(S1, NP - nl - nh, &tables);
+				if (nl) atomicAdd(&blk_counters[item_layer * 2 + 0], (unsigned long long) nl);
+				if (nh) atomicAdd(&blk_counters[item_layer * 2 + 1], (unsigned long long) nh);
+			}
+			// result index -> index of the pixel in the band (what the general kernel's list holds)
+			leftover_push(list, punt, (unsigned int) ((size_t) item_layer * b.out_rows * W
+					+ (w[10] - (size_t) item_layer * p.out_layer_stride) - (size_t) (b.out_row0 - p.out_buf_row0) * W), lane);
+			const unsigned int mask = __ballot_sync(0xffffffffu, again);
+			if (again) {
+				const int dst_slot = qcount + __popc(mask & ((1u << lane) - 1));
+#pragma unroll
+				for (int k = 0; k < 7; k++) queue[k][dst_slot] = w[k];
+				queue[7][dst_slot] = (unsigned int) S1;
+				queue[8][dst_slot] = (unsigned int) Q1;
+				queue[9][dst_slot] = (unsigned int) (Q1 >> 32);
+				queue[10][dst_slot] = w[10];
+				queue[11][dst_slot] = (unsigned int) nl | ((unsigned int) nh << 4) | ((unsigned int) item_layer << 8);
+			}
+			qcount += __popc(mask);
+			__syncwarp();
+		}
+		if (!more) break;
+	}
 	}	// tiles
 	__syncthreads();
 	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
@@ -422,7 +539,8 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 	const ssc_band &b = p.band;
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * (b.width >> 1);
 	if (total == 0) return SSC_OK;
-	const size_t smem = (size_t) NP * FAST_THREADS * sizeof(unsigned int);
+	const size_t smem = (size_t) NP * FAST_THREADS * sizeof(unsigned int)
+			+ (MODE == MODE_SIGMA_REG ? (size_t) (FAST_THREADS / 32) * FAST_QUEUE_WORDS * FAST_QUEUE_CAP * sizeof(unsigned int) : 0);
 	if (cudaFuncSetAttribute(k_stack_fast<NP, FULL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
 	const unsigned long long tiles = (total + FAST_THREADS - 1) / FAST_THREADS;
@@ -439,14 +557,15 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 		const unsigned long long cap = (unsigned long long) sms * per_sm * waves;
 		if (blocks > cap) blocks = cap;
 	}
-	LeftoverList list{nullptr, 0, nullptr, nullptr};
+	LeftoverList list{nullptr, 0, nullptr, nullptr, nullptr};
 	if (MODE == MODE_SIGMA_REG) {
-		int rc = leftover_list(NP, total * 2, list, stream);
+		int rc = leftover_ids(total * 2, list, stream);
 		if (rc) return rc;
 	}
 	k_stack_fast<NP, FULL, MODE><<<(unsigned int) blocks, FAST_THREADS, smem, stream>>>(p, list, (unsigned int) tiles);
 	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
-	if constexpr (MODE == MODE_SIGMA_REG) return launch_leftover<NP>(p, list, stream);
+	if constexpr (MODE == MODE_SIGMA_REG)	// the pixels that left the candidate window: general kernel, list mode
+		return launch_stack_generic(p, list.ids, list.count, list.capacity, 0, stream);
 	return SSC_OK;
 }
 

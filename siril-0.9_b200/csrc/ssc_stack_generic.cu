@@ -51,9 +51,9 @@ __global__ void k_stack_generic(StackParams p, PixelSource src, int n_pad, int i
 	const ssc_band &b = p.band;
 	const int W = b.width, N = b.n_frames;
 	unsigned long long total = src.list ? (unsigned long long) *src.list_count : src.total;
-	unsigned long long g = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
-
-	if (g < total) {
+	// (one pixel per thread when the grid covers the image; list mode loops with a bounded grid)
+	for (unsigned long long g = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; g < total;
+			g += (unsigned long long) gridDim.x * blockDim.x) {
 		unsigned long long pix = src.list ? src.list[g] : g;
 		int x = (int) (pix % W);
 		int rr = (int) ((pix / W) % b.out_rows);
@@ -131,7 +131,15 @@ int launch_stack_generic(const StackParams &p, const unsigned int *list, const u
 	src.total = (unsigned long long) b.layers * b.out_rows * b.width;
 	unsigned long long work = list ? list_capacity : src.total;
 	if (work == 0) return SSC_OK;
-	unsigned int grid = (unsigned int) ((work + block - 1) / block);
+	unsigned long long blocks = (work + block - 1) / block;
+	if (list) {	// the list is usually short and its length only known on the device
+		int dev = 0, sms = 148;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (blocks > (unsigned long long) sms * 8) blocks = (unsigned long long) sms * 8;
+	}
+	if (blocks > 0x7FFFFFFFull) return SSC_ERR_ARG;
+	unsigned int grid = (unsigned int) blocks;
 	k_stack_generic<<<grid, block, smem, stream>>>(p, src, n_pad, is_median);
 	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
 }

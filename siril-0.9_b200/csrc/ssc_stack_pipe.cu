@@ -382,7 +382,7 @@ static int launch_pipe_np(const StackParams &p, cudaStream_t stream) {
 	const size_t smem = sizeof(PipeSlot<NP>) * PIPE_SORTERS * PIPE_SLOTS;
 	if (cudaFuncSetAttribute(k_stack_pipe<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
-	LeftoverList list{nullptr, 0, nullptr, nullptr};
+	LeftoverList list{nullptr, 0, nullptr, nullptr, nullptr};
 	int rc = leftover_list(NP, total * 2, list, stream);
 	if (rc) return rc;
 	int dev = 0, sms = 148;
