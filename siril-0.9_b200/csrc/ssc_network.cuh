@@ -41,7 +41,11 @@ template <int KIND>
 __device__ __forceinline__ unsigned int normalize_pair_fast(unsigned int w, double off, double mul, double sc,
 		unsigned long long &Qa, unsigned long long &Qb) {
 	// I2F.F64.U16 reads either half of the packed word directly (conversion unit, off the ALU pipe)
+#ifdef SSC_NORM_MAGIC_IN
+	double da = word_to_double(w & 0xFFFFu), db = word_to_double(w >> 16);
+#else
 	double da = (double) (unsigned short) (w & 0xFFFFu), db = (double) (unsigned short) (w >> 16);
+#endif
 	if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) {
 		da = dmul(da, sc);
 		db = dmul(db, sc);
@@ -56,7 +60,7 @@ __device__ __forceinline__ unsigned int normalize_pair_fast(unsigned int w, doub
 	const unsigned int ra = round_to_word_fast(da), rb = round_to_word_fast(db);
 	Qa += (unsigned long long) ra * ra;	// IMAD.WIDE on the values while they are still unpacked
 	Qb += (unsigned long long) rb * rb;
-	return ra | (rb << 16);
+	return __byte_perm(ra, rb, 0x5410);	// one PRMT: ra | rb << 16 (both below 2^16)
 }
 
 }  // namespace ssc

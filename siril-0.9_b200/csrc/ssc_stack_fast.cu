@@ -56,23 +56,33 @@ enum { MODE_MEDIAN = 0, MODE_NOREJ = 1, MODE_SIGMA_REG = 2, MODE_QUEUE = 3 };
 template <int NP, int KIND>
 __device__ __forceinline__ void normalize_staged(unsigned int *stage_t, int stride, const double *s_coef,
 		unsigned int &Sa, unsigned int &Sb, unsigned long long &Qa, unsigned long long &Qb) {
-#pragma unroll 4
-	for (int f = 0; f < NP; f++) {
-		unsigned int w = stage_t[f * stride];
-		if constexpr (KIND != NO_NORM) {
-			double off = 0.0, mul = 1.0, sc = 1.0;
-			if constexpr (KIND == ADDITIVE || KIND == ADDITIVE_SCALING) off = s_coef[f];
-			if constexpr (KIND == MULTIPLICATIVE || KIND == MULTIPLICATIVE_SCALING) mul = s_coef[64 + f];
-			if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) sc = s_coef[128 + f];
-			w = normalize_pair_fast<KIND>(w, off, mul, sc, Qa, Qb);
-			stage_t[f * stride] = w;
-		} else {
-			const unsigned int pa = w & 0xFFFFu, pb = w >> 16;
-			Qa += (unsigned long long) pa * pa;
-			Qb += (unsigned long long) pb * pb;
+	static_assert(NP % 4 == 0, "groups of four frames");
+#pragma unroll 1
+	for (int f0 = 0; f0 < NP; f0 += 4) {
+		// all loads of a group first: the coefficient loads are off the critical path of the FP64 chain
+		unsigned int w[4];
+		double off[4], mul[4], sc[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			w[j] = stage_t[(f0 + j) * stride];
+			off[j] = 0.0; mul[j] = 1.0; sc[j] = 1.0;
+			if constexpr (KIND == ADDITIVE || KIND == ADDITIVE_SCALING) off[j] = s_coef[f0 + j];
+			if constexpr (KIND == MULTIPLICATIVE || KIND == MULTIPLICATIVE_SCALING) mul[j] = s_coef[64 + f0 + j];
+			if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) sc[j] = s_coef[128 + f0 + j];
 		}
-		Sa = __dp2a_lo(w, 0x0001u, Sa);		// IDP.2A: acc + lo16 * 1 + hi16 * 0
-		Sb = __dp2a_lo(w, 0x0100u, Sb);
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			if constexpr (KIND != NO_NORM) {
+				w[j] = normalize_pair_fast<KIND>(w[j], off[j], mul[j], sc[j], Qa, Qb);
+				stage_t[(f0 + j) * stride] = w[j];
+			} else {
+				const unsigned int pa = w[j] & 0xFFFFu, pb = w[j] >> 16;
+				Qa += (unsigned long long) pa * pa;
+				Qb += (unsigned long long) pb * pb;
+			}
+			Sa = __dp2a_lo(w[j], 0x0001u, Sa);		// IDP.2A: acc + lo16 * 1 + hi16 * 0
+			Sb = __dp2a_lo(w[j], 0x0100u, Sb);
+		}
 	}
 }
 
@@ -94,6 +104,13 @@ __device__ __forceinline__ bool clip_cannot_fire(unsigned long long S, unsigned 
 	return (d_lo == 0 || (float) d_lo < t_lo) && (d_hi == 0 || (float) d_hi < t_hi);
 }
 
+#ifndef SSC_STAGE_ROUNDS
+#define SSC_STAGE_ROUNDS 1
+#endif
+#ifndef SSC_FAST_CTAS
+#define SSC_FAST_CTAS 4
+#endif
+constexpr int FAST_STAGE_ROUNDS = SSC_STAGE_ROUNDS;
 constexpr int FAST_QUEUE_WORDS = 12, FAST_QUEUE_CAP = 96;	// per warp: < 32 waiting + up to 64 new per tile
 
 // FULL: n_frames == NP (no sentinel padding, no per-frame bound checks in the unrolled code)
@@ -105,7 +122,7 @@ constexpr int FAST_QUEUE_WORDS = 12, FAST_QUEUE_CAP = 96;	// per warp: < 32 wait
 constexpr int FAST_THREADS = SSC_FAST_THREADS;
 
 template <int NP, bool FULL, int MODE>
-__global__ void __launch_bounds__(FAST_THREADS, 512 / FAST_THREADS)
+__global__ void __launch_bounds__(FAST_THREADS, MODE == MODE_SIGMA_REG ? SSC_FAST_CTAS : 512 / FAST_THREADS)
 k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	extern __shared__ unsigned int cols[];		// [NP][FAST_THREADS] packed columns
 	__shared__ double s_coef[3 * 64];
@@ -126,9 +143,10 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	// MODE_SIGMA_REG: the dynamic shared memory holds the per-warp queues of pixels whose clipping
 	// has to be evaluated exactly, [warp][FAST_QUEUE_WORDS][FAST_QUEUE_CAP]
 	// behind the staging buffer [NP][FAST_THREADS] (see normalize_staged)
-	unsigned int (*queue)[FAST_QUEUE_CAP] = reinterpret_cast<unsigned int (*)[FAST_QUEUE_CAP]>(cols + NP * FAST_THREADS)
+	unsigned int (*queue)[FAST_QUEUE_CAP] = reinterpret_cast<unsigned int (*)[FAST_QUEUE_CAP]>(cols + NP / FAST_STAGE_ROUNDS * FAST_THREADS)
 			+ (tid >> 5) * FAST_QUEUE_WORDS;
 	int qcount = 0;		// items on this warp's queue (warp-uniform)
+	unsigned int lane_rej[6] = {0, 0, 0, 0, 0, 0};	// this lane's share of irej[3][2] (MODE_SIGMA_REG)
 	const float sig_low_f = (float) p.sig_low, sig_high_f = (float) p.sig_high;
 
 	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
@@ -153,6 +171,39 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	__syncthreads();
 
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * W2;
+#ifdef SSC_PINGPONG
+	static_assert(FAST_THREADS == 256, "ping-pong pairs warps w and w + 4");
+	if (MODE == MODE_SIGMA_REG && ((tid >> 7) & 1) && blockIdx.x < n_tiles && !(norm && !s_fast_norm))
+		asm volatile("bar.arrive %0, 64;" :: "r"(1 + 2 * ((tid >> 5) & 3)) : "memory");	// the first warp of each pair starts
+#endif
+	// MODE_SIGMA_REG: request a tile's samples (see the gather below); pf_* describe the requested tile
+	int pf_layer = 0;
+	unsigned int pf_out_idx = 0;
+	const bool punt_all = MODE == MODE_SIGMA_REG && norm && !s_fast_norm;
+	auto issue_tile = [&](unsigned long long t) {
+		// (the launcher guarantees 32-bit pixel counts and frame strides: no 64-bit division)
+		unsigned long long gg = t * FAST_THREADS + tid;
+		if (gg >= total) gg = total - 1;
+		const unsigned int g32 = (unsigned int) gg, row = g32 / (unsigned int) W2;
+		const int x2 = (int) (g32 - row * (unsigned int) W2);
+		const int lay = (int) (row / (unsigned int) b.out_rows);
+		const int rr = (int) (row - (unsigned int) lay * (unsigned int) b.out_rows);
+		const int R = b.out_row0 + rr;				// result storage row (stacking.c:731,1600)
+		const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - R : R;
+		const unsigned int toff = (unsigned int) ((((size_t) lay * b.layer_stride + (size_t) (srow - b.buf_row0) * W) >> 1) + x2);
+		pf_layer = lay;
+		pf_out_idx = (unsigned int) ((size_t) lay * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W + 2 * x2);
+		const char *src0 = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames) + toff);
+		const unsigned int fstride32 = (unsigned int) (b.frame_stride * sizeof(WORD));
+		const unsigned int sbase = (unsigned int) __cvta_generic_to_shared(cols + tid);
+#pragma unroll 4
+		for (int k = 0; k < NP; k++) {
+			const char *src = src0 + (unsigned long long) ((unsigned int) k) * fstride32;	// one IMAD.WIDE
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sbase + k * FAST_THREADS * (int) sizeof(unsigned int)), "l"(src) : "memory");
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	if (MODE == MODE_SIGMA_REG && !punt_all && blockIdx.x < n_tiles) issue_tile(blockIdx.x);
 	// Blocks loop over tiles (the launcher bounds the grid): the tables, the coefficient copy and
 	// their barriers above are paid once per block instead of once per tile.
 	// (MODE_SIGMA_REG runs one more round after its last tile, to drain the warp queues)
@@ -166,51 +217,29 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	unsigned long long g = tile * FAST_THREADS + tid;
 	const bool active = g < total;
 	if constexpr (MODE == MODE_SIGMA_REG) {
-		if (norm && !s_fast_norm) {	// coefficients outside the fast normalization's domain (block-uniform):
+		if (punt_all) {	// coefficients outside the fast normalization's domain (block-uniform):
 			leftover_push(list, active, (unsigned int) (2 * g), lane);		// every pixel goes to the
 			leftover_push(list, active, (unsigned int) (2 * g + 1), lane);	// general kernel
 			continue;
 		}
 	}
-	if (!active) g = total - 1;
-	int x2, rr, layer;
-	if constexpr (MODE == MODE_SIGMA_REG) {	// (the launcher guarantees 32-bit pixel counts: no 64-bit division)
-		const unsigned int g32 = (unsigned int) g, row = g32 / (unsigned int) W2;
-		x2 = (int) (g32 - row * (unsigned int) W2);
-		layer = (int) (row / (unsigned int) b.out_rows);
-		rr = (int) (row - (unsigned int) layer * (unsigned int) b.out_rows);
-	} else {
-		x2 = (int) (g % W2);
-		rr = (int) ((g / W2) % b.out_rows);
-		layer = (int) (g / ((unsigned long long) W2 * b.out_rows));
-	}
-	const int R = b.out_row0 + rr;				// result storage row (stacking.c:731,1600)
-	const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - R : R;
-	// per-thread offset inside a frame (32 bits: a frame holds < 2^32 pixel pairs) on top of a
-	// block-uniform per-frame base, so the 64 address computations stay off the ALU pipe
-	const unsigned int toff = (unsigned int) ((((size_t) layer * b.layer_stride + (size_t) (srow - b.buf_row0) * W) >> 1) + x2);
-	const unsigned int out_idx = (unsigned int) ((size_t) layer * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W + 2 * x2);
-	const unsigned int *frames32 = reinterpret_cast<const unsigned int *>(b.frames);
-	const size_t fstride2 = b.frame_stride >> 1;
-
+	int layer;
+	unsigned int out_idx;
 	unsigned int v[NP];
-	const char *ptr = reinterpret_cast<const char *>(frames32 + toff);
-	const size_t fstride_bytes = fstride2 * sizeof(unsigned int);
 	unsigned long long Qa = 0, Qb = 0;	// exact sums of squares of the (normalized) samples
 	unsigned int Sa = 0, Sb = 0;		// exact sums (fit 32 bits)
 	bool have_q = false;
+	const char *ptr = nullptr;
+	size_t fstride_bytes = 0;
 	if constexpr (MODE == MODE_SIGMA_REG) {
-		// ---- gather: one asynchronous 4-byte copy per frame straight into the thread's staging
-		// column (all in flight at once), then normalization and the sums in a rolled loop over it
+		// ---- this tile's samples were requested a tile ago (issue_tile): asynchronous 4-byte copies,
+		// one per frame, straight into the thread's staging column.  Normalization and the sums run
+		// in a rolled loop over the column, the network gets it through 64 static loads -- and as
+		// soon as the column is in registers the NEXT tile's copies are issued, to land under the
+		// network and the rejection.
+		layer = pf_layer;
+		out_idx = pf_out_idx;
 		unsigned int *stage_t = cols + tid;
-		unsigned int sdst = (unsigned int) __cvta_generic_to_shared(stage_t);
-#pragma unroll 4
-		for (int f = 0; f < NP; f++) {
-			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sdst), "l"(ptr) : "memory");
-			sdst += FAST_THREADS * sizeof(unsigned int);
-			ptr += fstride_bytes;
-		}
-		asm volatile("cp.async.commit_group;" ::: "memory");
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		switch (norm ? p.normalize : NO_NORM) {
 		case NO_NORM: normalize_staged<NP, NO_NORM>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
@@ -219,10 +248,23 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 		case ADDITIVE_SCALING: normalize_staged<NP, ADDITIVE_SCALING>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
 		default: normalize_staged<NP, MULTIPLICATIVE_SCALING>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
 		}
-		have_q = true;
 #pragma unroll
-		for (int f = 0; f < NP; f++) v[f] = stage_t[f * FAST_THREADS];
+		for (int k = 0; k < NP; k++) v[k] = stage_t[k * FAST_THREADS];
+		have_q = true;
+		if (tile + gridDim.x < n_tiles) issue_tile(tile + gridDim.x);
 	} else {
+	if (!active) g = total - 1;
+	const int x2 = (int) (g % W2);
+	const int rr = (int) ((g / W2) % b.out_rows);
+	layer = (int) (g / ((unsigned long long) W2 * b.out_rows));
+	const int R = b.out_row0 + rr;				// result storage row (stacking.c:731,1600)
+	const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - R : R;
+	// per-thread offset inside a frame (32 bits: a frame holds < 2^32 pixel pairs) on top of a
+	// block-uniform per-frame base, so the 64 address computations stay off the ALU pipe
+	const unsigned int toff = (unsigned int) ((((size_t) layer * b.layer_stride + (size_t) (srow - b.buf_row0) * W) >> 1) + x2);
+	out_idx = (unsigned int) ((size_t) layer * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W + 2 * x2);
+	ptr = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames) + toff);
+	fstride_bytes = (b.frame_stride >> 1) * sizeof(unsigned int);
 	// ---- gather: one packed load per frame, all issued before first use ----
 #pragma unroll
 	for (int f = 0; f < NP; f++) {
@@ -319,7 +361,21 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 			// candidate window (a third low, a sixth high) goes to the leftover list.  With NP >= 32
 			// and at most 7 rejections the reference's "N - r <= 4" break (:1684) cannot be reached.
 			static_assert(FULL && NP >= 32 && (NP & (NP - 1)) == 0, "needs a full stack of 32 or 64 frames");
+#ifdef SSC_PINGPONG
+			// Ping-pong: warps w and w + 4 share a scheduler; only one of them runs the (ALU-bound)
+			// network at a time, the other one meanwhile stages and normalizes its next tile on the
+			// FP64 / conversion / load-store pipes.  Two named barriers per pair hand the turn over.
+			{
+				const int pair = (tid >> 5) & 3, second = (tid >> 7) & 1;
+				asm volatile("bar.sync %0, 64;" :: "r"(1 + 2 * pair + second) : "memory");	// wait for my turn
+				sort_network<NP>(v);
+				const bool last = tile + gridDim.x >= n_tiles;	// (block-uniform) nobody waits for the very last hand-over
+				if (!(second && last))
+					asm volatile("bar.arrive %0, 64;" :: "r"(1 + 2 * pair + (second ^ 1)) : "memory");	// the partner's turn
+			}
+#else
 			sort_network<NP>(v);
+#endif
 			bool need[2];
 #pragma unroll
 			for (int h = 0; h < 2; h++) {
@@ -494,8 +550,13 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 			const bool again = mine && !punt && !done;
 			if (done) {
 				p.out[w[10]] = (WORD) mean_to_word<true>(S1, NP - nl - nh, &tables);
-				if (nl) atomicAdd(&blk_counters[item_layer * 2 + 0], (unsigned long long) nl);
-				if (nh) atomicAdd(&blk_counters[item_layer * 2 + 1], (unsigned long long) nh);
+#pragma unroll
+				for (int c = 0; c < 3; c++) {	// per-lane counters (64-bit shared-memory atomics are CAS loops)
+					if (item_layer == c) {
+						lane_rej[2 * c] += (unsigned int) nl;
+						lane_rej[2 * c + 1] += (unsigned int) nh;
+					}
+				}
 			}
 			// result index -> index of the pixel in the band (what the general kernel's list holds)
 			leftover_push(list, punt, (unsigned int) ((size_t) item_layer * b.out_rows * W
@@ -517,6 +578,13 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 		if (!more) break;
 	}
 	}	// tiles
+	if constexpr (MODE == MODE_SIGMA_REG) {
+#pragma unroll
+		for (int k = 0; k < 6; k++) {
+			const unsigned int sum = __reduce_add_sync(0xffffffffu, lane_rej[k]);
+			if (lane == 0 && sum) atomicAdd(&blk_counters[k], (unsigned long long) sum);
+		}
+	}
 	__syncthreads();
 	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
 		atomicAdd(&p.counters[tid], blk_counters[tid]);
@@ -539,21 +607,23 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 	const ssc_band &b = p.band;
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * (b.width >> 1);
 	if (total == 0) return SSC_OK;
-	const size_t smem = (size_t) NP * FAST_THREADS * sizeof(unsigned int)
-			+ (MODE == MODE_SIGMA_REG ? (size_t) (FAST_THREADS / 32) * FAST_QUEUE_WORDS * FAST_QUEUE_CAP * sizeof(unsigned int) : 0);
+	const size_t smem = MODE == MODE_SIGMA_REG
+			? (size_t) (NP / FAST_STAGE_ROUNDS) * FAST_THREADS * sizeof(unsigned int)
+				+ (size_t) (FAST_THREADS / 32) * FAST_QUEUE_WORDS * FAST_QUEUE_CAP * sizeof(unsigned int)
+			: (size_t) NP * FAST_THREADS * sizeof(unsigned int);
 	if (cudaFuncSetAttribute(k_stack_fast<NP, FULL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
 	const unsigned long long tiles = (total + FAST_THREADS - 1) / FAST_THREADS;
 	if (tiles > 0x7FFFFFFFull) return SSC_ERR_ARG;
 	unsigned long long blocks = tiles;
-	{	// a bounded grid of looping blocks: 16 per resident slot measured best (SSC_FAST_WAVES overrides)
+	{	// a bounded grid of looping blocks: 4 per resident slot measured best (SSC_FAST_WAVES overrides)
 		int dev = 0, sms = 148, per_sm = 1;
 		cudaGetDevice(&dev);
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stack_fast<NP, FULL, MODE>, FAST_THREADS, smem) != cudaSuccess || per_sm < 1)
 			per_sm = 1;
 		static int waves = 0;
-		if (!waves) { const char *e = getenv("SSC_FAST_WAVES"); waves = e ? atoi(e) : 16; if (waves < 1) waves = 1; }
+		if (!waves) { const char *e = getenv("SSC_FAST_WAVES"); waves = e ? atoi(e) : 4; if (waves < 1) waves = 1; }
 		const unsigned long long cap = (unsigned long long) sms * per_sm * waves;
 		if (blocks > cap) blocks = cap;
 	}
@@ -578,7 +648,8 @@ static int launch_fast_np(const StackParams &p, int is_median, cudaStream_t stre
 		return full ? launch_fast_cfg<NP, true, MODE_NOREJ>(p, stream) : launch_fast_cfg<NP, false, MODE_NOREJ>(p, stream);
 	if constexpr (NP >= 32) {
 		// (non-negative parameters: a sample above the median is then never "low", one below never "high")
-		if (full && p.rejection == SIGMA && p.sig_low >= 0.0 && p.sig_high >= 0.0)
+		if (full && p.rejection == SIGMA && p.sig_low >= 0.0 && p.sig_high >= 0.0
+				&& (unsigned long long) p.band.frame_stride * sizeof(WORD) < 0xFFFFFFFFull)
 			return launch_fast_cfg<NP, true, MODE_SIGMA_REG>(p, stream);
 	}
 	return full ? launch_fast_cfg<NP, true, MODE_QUEUE>(p, stream) : launch_fast_cfg<NP, false, MODE_QUEUE>(p, stream);
