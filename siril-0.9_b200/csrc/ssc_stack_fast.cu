@@ -53,12 +53,12 @@ enum { MODE_MEDIAN = 0, MODE_NOREJ = 1, MODE_SIGMA_REG = 2, MODE_QUEUE = 3 };
 // instructions an SM serves at full rate (tools/micro/ifetch.cu: beyond that, issue drops to
 // ~0.3-0.6 warp-instructions per clock and scheduler whatever the pipes could do).
 // One thread's staging column: stage[f * FAST_THREADS + tid], conflict-free.
-template <int NP, int KIND>
-__device__ __forceinline__ void normalize_staged(unsigned int *stage_t, int stride, const double *s_coef,
+template <int NP, int KIND, bool FULL>
+__device__ __forceinline__ void normalize_staged(unsigned int *stage_t, int stride, const double *s_coef, int N,
 		unsigned int &Sa, unsigned int &Sb, unsigned long long &Qa, unsigned long long &Qb) {
 	static_assert(NP % 4 == 0, "groups of four frames");
 #pragma unroll 1
-	for (int f0 = 0; f0 < NP; f0 += 4) {
+	for (int f0 = 0; f0 < (FULL ? NP : N); f0 += 4) {
 		// all loads of a group first: the coefficient loads are off the critical path of the FP64 chain
 		unsigned int w[4];
 		double off[4], mul[4], sc[4];
@@ -72,6 +72,7 @@ __device__ __forceinline__ void normalize_staged(unsigned int *stage_t, int stri
 		}
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
+			if (!FULL && f0 + j >= N) break;	// (the words behind the N samples hold the 0xFFFF sentinels)
 			if constexpr (KIND != NO_NORM) {
 				w[j] = normalize_pair_fast<KIND>(w[j], off[j], mul[j], sc[j], Qa, Qb);
 				stage_t[(f0 + j) * stride] = w[j];
@@ -83,6 +84,20 @@ __device__ __forceinline__ void normalize_staged(unsigned int *stage_t, int stri
 			Sa = __dp2a_lo(w[j], 0x0001u, Sa);		// IDP.2A: acc + lo16 * 1 + hi16 * 0
 			Sb = __dp2a_lo(w[j], 0x0100u, Sb);
 		}
+	}
+}
+
+// Coefficients outside the domain of the fast form (|value| >= 2^31): the conversion-based one.
+__device__ __noinline__ void normalize_staged_slow(unsigned int *stage_t, int stride, const double *s_coef, int N, int mode,
+		unsigned int &Sa, unsigned int &Sb, unsigned long long &Qa, unsigned long long &Qb) {
+	for (int f = 0; f < N; f++) {
+		const unsigned int w = stage_t[f * stride];
+		const unsigned int pa = normalize_sample(w & 0xFFFFu, mode, s_coef[f], s_coef[64 + f], s_coef[128 + f]);
+		const unsigned int pb = normalize_sample(w >> 16, mode, s_coef[f], s_coef[64 + f], s_coef[128 + f]);
+		stage_t[f * stride] = pa | (pb << 16);
+		Sa += pa; Sb += pb;
+		Qa += (unsigned long long) pa * pa;
+		Qb += (unsigned long long) pb * pb;
 	}
 }
 
@@ -136,6 +151,12 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	__shared__ unsigned long long s_Q[2 * FAST_THREADS];
 
 
+	// STAGED: the samples travel through a shared-memory staging column and everything before the
+	// network is rolled code (64-frame stacks: their unrolled form overflows the instruction cache);
+	// PREFETCH: the next tile's copies are issued under the network (the staging buffer is free then)
+	constexpr bool STAGED = MODE == MODE_SIGMA_REG || NP == 64;
+	constexpr bool PREFETCH = MODE == MODE_SIGMA_REG;
+
 	const ssc_band &b = p.band;
 	const int W = b.width, N = FULL ? NP : b.n_frames, tid = threadIdx.x, lane = tid & 31;
 	const int W2 = W >> 1;
@@ -181,7 +202,7 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	unsigned int pf_out_idx = 0;
 	const bool punt_all = MODE == MODE_SIGMA_REG && norm && !s_fast_norm;
 	auto issue_tile = [&](unsigned long long t) {
-		// (the launcher guarantees 32-bit pixel counts and frame strides: no 64-bit division)
+		// (fast_path_eligible guarantees 32-bit pixel counts and frame strides: no 64-bit division)
 		unsigned long long gg = t * FAST_THREADS + tid;
 		if (gg >= total) gg = total - 1;
 		const unsigned int g32 = (unsigned int) gg, row = g32 / (unsigned int) W2;
@@ -198,12 +219,16 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 		const unsigned int sbase = (unsigned int) __cvta_generic_to_shared(cols + tid);
 #pragma unroll 4
 		for (int k = 0; k < NP; k++) {
-			const char *src = src0 + (unsigned long long) ((unsigned int) k) * fstride32;	// one IMAD.WIDE
-			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sbase + k * FAST_THREADS * (int) sizeof(unsigned int)), "l"(src) : "memory");
+			if (FULL || k < N) {
+				const char *src = src0 + (unsigned long long) ((unsigned int) k) * fstride32;	// one IMAD.WIDE
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sbase + k * FAST_THREADS * (int) sizeof(unsigned int)), "l"(src) : "memory");
+			} else {
+				cols[k * FAST_THREADS + tid] = 0xFFFFFFFFu;	// sentinels sort behind the N samples
+			}
 		}
 		asm volatile("cp.async.commit_group;" ::: "memory");
 	};
-	if (MODE == MODE_SIGMA_REG && !punt_all && blockIdx.x < n_tiles) issue_tile(blockIdx.x);
+	if (PREFETCH && !punt_all && blockIdx.x < n_tiles) issue_tile(blockIdx.x);
 	// Blocks loop over tiles (the launcher bounds the grid): the tables, the coefficient copy and
 	// their barriers above are paid once per block instead of once per tile.
 	// (MODE_SIGMA_REG runs one more round after its last tile, to drain the warp queues)
@@ -231,27 +256,32 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	bool have_q = false;
 	const char *ptr = nullptr;
 	size_t fstride_bytes = 0;
-	if constexpr (MODE == MODE_SIGMA_REG) {
-		// ---- this tile's samples were requested a tile ago (issue_tile): asynchronous 4-byte copies,
-		// one per frame, straight into the thread's staging column.  Normalization and the sums run
-		// in a rolled loop over the column, the network gets it through 64 static loads -- and as
-		// soon as the column is in registers the NEXT tile's copies are issued, to land under the
-		// network and the rejection.
+	if constexpr (STAGED) {
+		// ---- asynchronous 4-byte copies, one per frame, straight into the thread's staging column
+		// (issue_tile; with PREFETCH they were issued a tile ago).  Normalization and the sums run in
+		// a rolled loop over the column, the network gets it through NP static loads -- and with
+		// PREFETCH the NEXT tile's copies are issued as soon as the column is in registers, to land
+		// under the network and the rejection.
+		if constexpr (!PREFETCH) issue_tile(tile);
 		layer = pf_layer;
 		out_idx = pf_out_idx;
 		unsigned int *stage_t = cols + tid;
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
-		switch (norm ? p.normalize : NO_NORM) {
-		case NO_NORM: normalize_staged<NP, NO_NORM>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
-		case ADDITIVE: normalize_staged<NP, ADDITIVE>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
-		case MULTIPLICATIVE: normalize_staged<NP, MULTIPLICATIVE>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
-		case ADDITIVE_SCALING: normalize_staged<NP, ADDITIVE_SCALING>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
-		default: normalize_staged<NP, MULTIPLICATIVE_SCALING>(stage_t, FAST_THREADS, s_coef, Sa, Sb, Qa, Qb); break;
+		if (norm && !s_fast_norm) {
+			normalize_staged_slow(stage_t, FAST_THREADS, s_coef, N, p.normalize, Sa, Sb, Qa, Qb);
+		} else {
+			switch (norm ? p.normalize : NO_NORM) {
+			case NO_NORM: normalize_staged<NP, NO_NORM, FULL>(stage_t, FAST_THREADS, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case ADDITIVE: normalize_staged<NP, ADDITIVE, FULL>(stage_t, FAST_THREADS, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case MULTIPLICATIVE: normalize_staged<NP, MULTIPLICATIVE, FULL>(stage_t, FAST_THREADS, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case ADDITIVE_SCALING: normalize_staged<NP, ADDITIVE_SCALING, FULL>(stage_t, FAST_THREADS, s_coef, N, Sa, Sb, Qa, Qb); break;
+			default: normalize_staged<NP, MULTIPLICATIVE_SCALING, FULL>(stage_t, FAST_THREADS, s_coef, N, Sa, Sb, Qa, Qb); break;
+			}
 		}
 #pragma unroll
 		for (int k = 0; k < NP; k++) v[k] = stage_t[k * FAST_THREADS];
 		have_q = true;
-		if (tile + gridDim.x < n_tiles) issue_tile(tile + gridDim.x);
+		if (PREFETCH && tile + gridDim.x < n_tiles) issue_tile(tile + gridDim.x);
 	} else {
 	if (!active) g = total - 1;
 	const int x2 = (int) (g % W2);
@@ -321,7 +351,7 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	} else {
 		// exact integer sums of the (normalized) samples; the sum fits 32 bits and comes straight
 		// from the packed words (IDP.2A: acc + lo16 * 1 + hi16 * 0), the sum of squares needs 64
-		if constexpr (MODE != MODE_SIGMA_REG) {		// (MODE_SIGMA_REG: summed in the rolled loop)
+		if constexpr (!STAGED) {		// (STAGED: summed in the rolled loop)
 #pragma unroll
 			for (int f = 0; f < NP; f++) {
 				if (FULL || f < N) {
@@ -599,6 +629,7 @@ bool fast_path_eligible(const StackParams &p, int is_median) {
 	if ((b.width & 1) || (b.frame_stride & 1) || (b.layer_stride & 1)) return false;
 	if (((uintptr_t) b.frames & 3) || ((uintptr_t) p.out & 3) || (p.out_layer_stride & 1)) return false;
 	if ((size_t) b.layers * p.out_layer_stride >= 0xFFFFFFF0ull) return false;	// 32-bit result indices
+	if ((unsigned long long) b.frame_stride * sizeof(WORD) >= 0xFFFFFFF0ull) return false;	// 32-bit frame stride in bytes
 	return true;
 }
 
@@ -648,8 +679,7 @@ static int launch_fast_np(const StackParams &p, int is_median, cudaStream_t stre
 		return full ? launch_fast_cfg<NP, true, MODE_NOREJ>(p, stream) : launch_fast_cfg<NP, false, MODE_NOREJ>(p, stream);
 	if constexpr (NP >= 32) {
 		// (non-negative parameters: a sample above the median is then never "low", one below never "high")
-		if (full && p.rejection == SIGMA && p.sig_low >= 0.0 && p.sig_high >= 0.0
-				&& (unsigned long long) p.band.frame_stride * sizeof(WORD) < 0xFFFFFFFFull)
+		if (full && p.rejection == SIGMA && p.sig_low >= 0.0 && p.sig_high >= 0.0)
 			return launch_fast_cfg<NP, true, MODE_SIGMA_REG>(p, stream);
 	}
 	return full ? launch_fast_cfg<NP, true, MODE_QUEUE>(p, stream) : launch_fast_cfg<NP, false, MODE_QUEUE>(p, stream);
