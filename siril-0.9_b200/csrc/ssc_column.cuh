@@ -15,6 +15,7 @@
 // interior samples and compacts like the reference does.
 #pragma once
 #include "ssc_device.cuh"
+#include "ssc_kernels.h"
 
 namespace ssc {
 
@@ -100,7 +101,7 @@ __device__ __forceinline__ int sigma_pass_sorted(Column c, int &o, int &N, doubl
 template <bool SMALLN>
 static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int N, int rejection, double slow,
 		double shigh, unsigned long long S, unsigned long long Q, RejectState &st,
-		const SmallN *tables = nullptr) {
+		const SmallN *tables = nullptr, const FitTables *fit = nullptr) {
 	double sigma, median;
 	int n, r = 0, iter = 0, o = 0;
 
@@ -218,19 +219,34 @@ static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int
 		break;
 	case LINEARFIT:		// stacking.c:1750-1784
 		do {
-			// gsl_fit_linear with x_i = i (GSL fit/linear.c), literal running means
+			// gsl_fit_linear with x_i = i (GSL fit/linear.c), literal running means.  With the tables
+			// (FitTables) the data-independent recurrences (mean of x, mean of dx^2) are looked up and
+			// every division by i + 1 becomes div_exact() with RN(1 / (i + 1)): same bits, ~5x less work.
 			double m_x = 0.0, m_y = 0.0, m_dx2 = 0.0, m_dxdy = 0.0;
-			for (int i = 0; i < N; i++) {
-				double ip1 = dadd((double) i, 1.0);
-				m_x = dadd(m_x, ddiv(dsub((double) i, m_x), ip1));
-				m_y = dadd(m_y, ddiv(dsub((double) (int) c.get(i), m_y), ip1));
-			}
-			for (int i = 0; i < N; i++) {
-				double ip1 = dadd((double) i, 1.0);
-				double dx = dsub((double) i, m_x);
-				double dy = dsub((double) (int) c.get(i), m_y);
-				m_dx2 = dadd(m_dx2, ddiv(dsub(dmul(dx, dx), m_dx2), ip1));
-				m_dxdy = dadd(m_dxdy, ddiv(dsub(dmul(dx, dy), m_dxdy), ip1));
+			const bool tab = fit && N <= fit->n_max;
+			if (tab) {
+				m_x = fit->mx[N];
+				m_dx2 = fit->mdx2[N];
+				for (int i = 0; i < N; i++)
+					m_y = dadd(m_y, div_exact(dsub((double) (int) c.get(i), m_y), (double) (i + 1), fit->inv[i + 1]));
+				for (int i = 0; i < N; i++) {
+					double dx = dsub((double) i, m_x);
+					double dy = dsub((double) (int) c.get(i), m_y);
+					m_dxdy = dadd(m_dxdy, div_exact(dsub(dmul(dx, dy), m_dxdy), (double) (i + 1), fit->inv[i + 1]));
+				}
+			} else {
+				for (int i = 0; i < N; i++) {
+					double ip1 = dadd((double) i, 1.0);
+					m_x = dadd(m_x, ddiv(dsub((double) i, m_x), ip1));
+					m_y = dadd(m_y, ddiv(dsub((double) (int) c.get(i), m_y), ip1));
+				}
+				for (int i = 0; i < N; i++) {
+					double ip1 = dadd((double) i, 1.0);
+					double dx = dsub((double) i, m_x);
+					double dy = dsub((double) (int) c.get(i), m_y);
+					m_dx2 = dadd(m_dx2, ddiv(dsub(dmul(dx, dx), m_dx2), ip1));
+					m_dxdy = dadd(m_dxdy, ddiv(dsub(dmul(dx, dy), m_dxdy), ip1));
+				}
 			}
 			const double a = ddiv(m_dxdy, m_dx2);		// slope
 			const double b = dsub(m_y, dmul(m_x, a));	// intercept
@@ -238,10 +254,11 @@ static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int
 			for (int f = 0; f < N; f++)
 				sigma = dadd(sigma, fabs(dsub((double) (int) c.get(f), dadd(dmul(a, (double) f), b))));
 			sigma = ddiv(sigma, (double) N);
+			const Reciprocal inv_sigma(sigma);	// line_clipping divides every residual by sigma (:1175,1179)
 			int out = 0, f = 0;
 			for (; f < N; f++) {
 				unsigned int v = c.get(f);
-				int fl = clip_line(v, slow, shigh, sigma, f, a, b);
+				int fl = clip_line(inv_sigma, v, slow, shigh, f, a, b);
 				if (fl) {
 					r++; S -= v;
 					if (fl < 0) st.rej_lo++; else st.rej_hi++;

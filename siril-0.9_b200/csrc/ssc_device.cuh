@@ -109,7 +109,37 @@ __device__ __forceinline__ int clip_percentile(unsigned int p, double plow, doub
 	return 0;
 }
 
+// a / b correctly rounded for a divisor that is used many times: y = RN(1 / b) is computed once
+// (one real division), then Markstein's sequence as in div_exact().  The theorem excludes divisors
+// whose significand is all ones, and the intermediate products must stay normal: anything else
+// (b zero, subnormal, huge, NaN ...) keeps the plain division.
+struct Reciprocal {
+	double b, y;
+	bool ok;
+	__device__ __forceinline__ explicit Reciprocal(double divisor) : b(divisor) {
+		const unsigned int hi = (unsigned int) __double2hiint(divisor), lo = (unsigned int) __double2loint(divisor);
+		const unsigned int e = (hi >> 20) & 0x7FFu;
+		ok = e > 1023u - 200u && e < 1023u + 200u && !((hi & 0xFFFFFu) == 0xFFFFFu && lo == 0xFFFFFFFFu);
+		y = ok ? ddiv(1.0, divisor) : 0.0;
+	}
+	// |a| must be 0 or within 2^+-200 too (the callers divide pixel-scale residuals)
+	__device__ __forceinline__ double divide(double a) const {
+		if (!ok) return ddiv(a, b);
+		const double q0 = dmul(a, y);
+		const double r = __fma_rn(-b, q0, a);
+		return __fma_rn(r, y, q0);
+	}
+};
+
 // line_clipping, stacking.c:1170-1183
+__device__ __forceinline__ int clip_line(const Reciprocal &inv_sigma, unsigned int p, double slow, double shigh, int i,
+		double a, double b) {
+	double x = (double) (int) p, xi = (double) i;
+	if (inv_sigma.divide(dsub(dadd(dmul(a, xi), b), x)) > slow) return -1;
+	if (inv_sigma.divide(dsub(dsub(x, dmul(a, xi)), b)) > shigh) return 1;
+	return 0;
+}
+
 __device__ __forceinline__ int clip_line(unsigned int p, double slow, double shigh, double sigma, int i,
 		double a, double b) {
 	double x = (double) (int) p, xi = (double) i;

@@ -8,6 +8,15 @@
 
 namespace ssc {
 
+// Tables that take the divisions out of the linear-fit rejection without changing a bit
+// (ssc_column.cuh, LINEARFIT): device arrays indexed by n = 1..n_max.
+struct FitTables {
+	const double *inv;	// RN(1 / n)
+	const double *mx;	// gsl_fit_linear's running mean of x_i = i after n steps (data independent)
+	const double *mdx2;	// its running mean of (i - mx[n])^2 after n steps
+	int n_max;		// 0: no tables, literal divisions
+};
+
 struct StackParams {
 	ssc_band band;
 	int normalize;
@@ -18,6 +27,7 @@ struct StackParams {
 	size_t out_layer_stride;
 	int out_buf_row0;
 	unsigned long long *counters;	// device uint64[SSC_COUNTERS] or nullptr
+	FitTables fit;			// filled by launch_stack() for LINEARFIT
 };
 
 // ssc_stack_generic.cu

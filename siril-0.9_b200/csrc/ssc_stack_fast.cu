@@ -506,7 +506,7 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 				Column c{cols16 + item, 2 * FAST_THREADS};
 				RejectState ist{0, 0, 0, 0};
 				const unsigned int r = reject_sorted_and_mean<true>(c, N, p.rejection, p.sig_low, p.sig_high,
-						s_S[item], s_Q[item], ist, &tables);
+						s_S[item], s_Q[item], ist, &tables, &p.fit);
 				s_res[item] = (unsigned short) r;
 				const int il = s_layer[item >> 1];
 				if (ist.rej_lo) atomicAdd(&blk_counters[il * 2 + 0], (unsigned long long) ist.rej_lo);

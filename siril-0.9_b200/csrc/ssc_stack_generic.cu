@@ -98,7 +98,7 @@ __global__ void k_stack_generic(StackParams p, PixelSource src, int n_pad, int i
 			int lhs = (N - 1) >> 1, rhs = N >> 1;
 			result = (c.get(lhs) + c.get(rhs)) >> 1;
 		} else {
-			result = reject_sorted_and_mean<false>(c, N, p.rejection, p.sig_low, p.sig_high, S, Q, st);
+			result = reject_sorted_and_mean<false>(c, N, p.rejection, p.sig_low, p.sig_high, S, Q, st, nullptr, &p.fit);
 		}
 		p.out[(size_t) layer * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W + x] = (WORD) result;
 
@@ -144,9 +144,57 @@ int launch_stack_generic(const StackParams &p, const unsigned int *list, const u
 	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------------------
+// FitTables (ssc_kernels.h): built once per device with the literal recurrences of gsl_fit_linear
+// for x_i = i, so that looking them up gives the very bits the per-pixel loops would compute.
+// ---------------------------------------------------------------------------
+__global__ void k_fit_tables(double *inv, double *mx, double *mdx2, int n_max) {
+	const int n = blockIdx.x * blockDim.x + threadIdx.x;
+	if (n > n_max) return;
+	if (n == 0) { inv[0] = 0.0; mx[0] = 0.0; mdx2[0] = 0.0; return; }
+	inv[n] = ddiv(1.0, (double) n);
+	double m_x = 0.0, m_dx2 = 0.0;
+	for (int i = 0; i < n; i++) m_x = dadd(m_x, ddiv(dsub((double) i, m_x), dadd((double) i, 1.0)));
+	for (int i = 0; i < n; i++) {
+		const double dx = dsub((double) i, m_x);
+		m_dx2 = dadd(m_dx2, ddiv(dsub(dmul(dx, dx), m_dx2), dadd((double) i, 1.0)));
+	}
+	mx[n] = m_x;
+	mdx2[n] = m_dx2;
+}
+
+static double *g_fit_store[64];	// per device: [3][SSC_GENERIC_MAX_FRAMES + 1]
+
+static int fit_tables(FitTables &fit, cudaStream_t stream) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) return SSC_ERR_ARG;
+	const int n_max = SSC_GENERIC_MAX_FRAMES, stride = n_max + 1;
+	if (!g_fit_store[dev]) {
+		double *t = nullptr;
+		if (cudaMalloc(&t, (size_t) 3 * stride * sizeof(double)) != cudaSuccess) return SSC_ERR_CUDA;
+		// built on the launching stream: ordered before the kernel that reads it; later launches on
+		// other streams of this device come after this call returned, hence the synchronisation
+		k_fit_tables<<<(stride + 127) / 128, 128, 0, stream>>>(t, t + stride, t + 2 * stride, n_max);
+		if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { cudaFree(t); return SSC_ERR_CUDA; }
+		g_fit_store[dev] = t;
+	}
+	fit.inv = g_fit_store[dev];
+	fit.mx = g_fit_store[dev] + stride;
+	fit.mdx2 = g_fit_store[dev] + 2 * stride;
+	fit.n_max = n_max;
+	return SSC_OK;
+}
+
 int g_kernel_path = 0;
 
-int launch_stack(const StackParams &p, int is_median, cudaStream_t stream) {
+int launch_stack(const StackParams &p_in, int is_median, cudaStream_t stream) {
+	StackParams p = p_in;
+	p.fit = FitTables{nullptr, nullptr, nullptr, 0};
+	if (!is_median && p.rejection == LINEARFIT) {
+		int rc = fit_tables(p.fit, stream);
+		if (rc) return rc;
+	}
 	if (g_kernel_path == 2 && pipe_path_eligible(p, is_median))
 		return launch_stack_pipe(p, stream);	// experimental (slower than the register kernel so far)
 	if (g_kernel_path != 1 && fast_path_eligible(p, is_median))
