@@ -374,7 +374,7 @@ def main():
             config=dict(workload=CFG["name"], frames=n, width=w, height=h, channels=c,
                         parallelism="row bands x%d" % world, l2="inputs (9.2 GB) exceed L2 (126 MB): no flush needed",
                         seed=hex(SEED), rejection_counters=irej.tolist(), guard_fired=guard, cap_hit=cap),
-            roofline=dict(bound="hbm", kernel="k_stack_fast<64,true,256> (K3: normalize + sigma-clip + mean, register sorting network)",
+            roofline=dict(bound="hbm", kernel="k_stack_fast<64,true,SIGMA_REG> (K3: normalize + sigma-clip + mean, register sorting network)",
                           achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
                           peak_source=peak_src, algorithmic_bytes_per_launch=bytes_stack,
                           ms_per_launch=ms_stack),
