@@ -199,6 +199,8 @@ int launch_stack(const StackParams &p_in, int is_median, cudaStream_t stream) {
 		return launch_stack_pipe(p, stream);	// experimental (slower than the register kernel so far)
 	if (g_kernel_path != 1 && fast_path_eligible(p, is_median))
 		return launch_stack_fast(p, is_median, stream);
+	if (g_kernel_path != 1 && mid_path_eligible(p, is_median))
+		return launch_stack_mid(p, is_median, stream);
 	return launch_stack_generic(p, nullptr, nullptr, 0, is_median, stream);
 }
 

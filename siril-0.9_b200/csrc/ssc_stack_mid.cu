@@ -1,0 +1,272 @@
+// ssc_stack_mid.cu -- K2/K3 for stacks of 65..256 frames without registration shifts (the deep-sky
+// shape of BASELINE.json's cfg4: 200 frames, winsorized rejection).
+//
+// The same two-pixels-per-thread packed u16x2 columns as ssc_stack_fast.cu, but a column no longer fits
+// the register file, so it lives in shared memory (col[i][thread], conflict-free) and is sorted in pieces:
+//   1. one asynchronous 4-byte copy per frame lands the raw samples in the column, all in flight at once;
+//   2. a rolled loop normalizes them in place (exact FP64, as in the 64-frame kernel) and takes the sums;
+//   3. every run of 64 samples goes through the REGISTER sorting network (64 static loads, 543 packed
+//      compare-exchanges, 64 static stores) -- the network's code is instantiated once and looped over;
+//   4. the sorted runs are merged pairwise with bitonic merges: the long-distance stages are rolled loops
+//      over shared memory (the partner of element k of one run is element L-1-k of the other), the last
+//      six stages of every 64-element block run in registers again (192 compare-exchanges);
+//   5. the sorted column goes through the same per-pixel rejection code as the general kernel
+//      (ssc_column.cuh), one pixel of the pair after the other.
+// Per pixel this is ~9 k instructions against ~50 k for the general kernel's shared-memory bitonic sort.
+#include "ssc_column.cuh"
+#include "ssc_kernels.h"
+#include "ssc_network.cuh"
+
+namespace ssc {
+
+constexpr int MID_THREADS = 64;
+
+// the last six stages of a bitonic merge: v[0..64) bitonic -> ascending
+__device__ __forceinline__ void bitonic_merge_64(unsigned int (&v)[64]) {
+#pragma unroll
+	for (int d = 32; d >= 1; d >>= 1) {
+#pragma unroll
+		for (int i = 0; i < 64; i++) {
+			if ((i & d) == 0) {
+				const unsigned int lo = __vminu2(v[i], v[i + d]);
+				v[i + d] = __vmaxu2(v[i], v[i + d]);
+				v[i] = lo;
+			}
+		}
+	}
+}
+
+template <int KIND>
+__device__ __forceinline__ void normalize_column(unsigned int *col_t, const double *s_coef, int N,
+		unsigned int &Sa, unsigned int &Sb, unsigned long long &Qa, unsigned long long &Qb) {
+#pragma unroll 1
+	for (int f0 = 0; f0 < N; f0 += 4) {
+		unsigned int w[4];
+		double off[4], mul[4], sc[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {	// (the column and the coefficient arrays are padded to a multiple of 4)
+			w[j] = col_t[(f0 + j) * MID_THREADS];
+			off[j] = 0.0; mul[j] = 1.0; sc[j] = 1.0;
+			if constexpr (KIND == ADDITIVE || KIND == ADDITIVE_SCALING) off[j] = s_coef[f0 + j];
+			if constexpr (KIND == MULTIPLICATIVE || KIND == MULTIPLICATIVE_SCALING) mul[j] = s_coef[256 + f0 + j];
+			if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) sc[j] = s_coef[512 + f0 + j];
+		}
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			if (f0 + j >= N) break;
+			if constexpr (KIND != NO_NORM) {
+				w[j] = normalize_pair_fast<KIND>(w[j], off[j], mul[j], sc[j], Qa, Qb);
+				col_t[(f0 + j) * MID_THREADS] = w[j];
+			} else {
+				const unsigned int pa = w[j] & 0xFFFFu, pb = w[j] >> 16;
+				Qa += (unsigned long long) pa * pa;
+				Qb += (unsigned long long) pb * pb;
+			}
+			Sa = __dp2a_lo(w[j], 0x0001u, Sa);
+			Sb = __dp2a_lo(w[j], 0x0100u, Sb);
+		}
+	}
+}
+
+// NPAD: 128 or 256, the column length the merges work on (sentinels 0xFFFF behind the N samples)
+template <int NPAD>
+__global__ void __launch_bounds__(MID_THREADS)
+k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
+	extern __shared__ unsigned int col[];			// [NPAD][MID_THREADS] packed columns
+	__shared__ double s_coef[3 * 256];			// offset, mul, scale
+	__shared__ int s_fast_norm;
+	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
+
+	const ssc_band &b = p.band;
+	const int W = b.width, W2 = W >> 1, N = b.n_frames, tid = threadIdx.x;
+	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
+	const bool need_sort = is_median || p.rejection != NO_REJEC;
+
+	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
+	if (tid == 0) s_fast_norm = 1;
+	__syncthreads();
+	for (int f = tid; f < 256; f += MID_THREADS) {
+		const bool have = norm && f < N;
+		const double off = have ? p.coeff[f] : 0.0, mul = have ? p.coeff[N + f] : 1.0, sc = have ? p.coeff[2 * N + f] : 1.0;
+		s_coef[f] = off;
+		s_coef[256 + f] = mul;
+		s_coef[512 + f] = sc;
+		if (have) {	// domain of the 2^52 tricks (ssc_network.cuh): every intermediate stays below 2^31
+			const bool additive = p.normalize == ADDITIVE || p.normalize == ADDITIVE_SCALING;
+			const double bound = additive ? dadd(dmul(fabs(sc), 65535.0), fabs(off)) : dmul(dmul(fabs(sc), 65535.0), fabs(mul));
+			if (!(bound < 2147483000.0)) s_fast_norm = 0;
+		}
+	}
+	__syncthreads();
+
+	const unsigned int total = (unsigned int) ((unsigned long long) b.layers * b.out_rows * W2);	// < 2^32: mid_path_eligible
+	unsigned int *col_t = col + tid;
+	const unsigned int sbase = (unsigned int) __cvta_generic_to_shared(col_t);
+	const unsigned int fstride32 = (unsigned int) (b.frame_stride * sizeof(WORD));
+
+	for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		unsigned int g = tile * MID_THREADS + tid;
+		const bool active = g < total;
+		if (!active) g = total - 1;
+		const unsigned int row = g / (unsigned int) W2;
+		const int x2 = (int) (g - row * (unsigned int) W2);
+		const int layer = (int) (row / (unsigned int) b.out_rows);
+		const int rr = (int) (row - (unsigned int) layer * (unsigned int) b.out_rows);
+		const int R = b.out_row0 + rr;				// result storage row (stacking.c:731,1600)
+		const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - R : R;
+		const unsigned int toff = (unsigned int) ((((size_t) layer * b.layer_stride + (size_t) (srow - b.buf_row0) * W) >> 1) + x2);
+		const unsigned int out_idx = (unsigned int) ((size_t) layer * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W + 2 * x2);
+		const char *src0 = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames) + toff);
+
+		// ---- 1. gather ----
+#pragma unroll 4
+		for (int f = 0; f < N; f++) {
+			const char *src = src0 + (unsigned long long) ((unsigned int) f) * fstride32;
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sbase + f * MID_THREADS * (int) sizeof(unsigned int)), "l"(src) : "memory");
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		for (int f = N; f < NPAD; f++) col_t[f * MID_THREADS] = 0xFFFFFFFFu;	// sentinels sort behind the samples
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+		// ---- 2. normalize in place (stacking.c:1635-1652; median path :750-764), exact sums ----
+		unsigned int Sa = 0, Sb = 0;
+		unsigned long long Qa = 0, Qb = 0;
+		if (norm && !s_fast_norm) {
+			for (int f = 0; f < N; f++) {
+				const unsigned int w = col_t[f * MID_THREADS];
+				const unsigned int pa = normalize_sample(w & 0xFFFFu, p.normalize, s_coef[f], s_coef[256 + f], s_coef[512 + f]);
+				const unsigned int pb = normalize_sample(w >> 16, p.normalize, s_coef[f], s_coef[256 + f], s_coef[512 + f]);
+				col_t[f * MID_THREADS] = pa | (pb << 16);
+				Sa += pa; Sb += pb;
+				Qa += (unsigned long long) pa * pa;
+				Qb += (unsigned long long) pb * pb;
+			}
+		} else {
+			switch (norm ? p.normalize : NO_NORM) {
+			case NO_NORM: normalize_column<NO_NORM>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case ADDITIVE: normalize_column<ADDITIVE>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case MULTIPLICATIVE: normalize_column<MULTIPLICATIVE>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case ADDITIVE_SCALING: normalize_column<ADDITIVE_SCALING>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
+			default: normalize_column<MULTIPLICATIVE_SCALING>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
+			}
+		}
+
+		if (need_sort) {
+			// ---- 3. runs of 64 through the register network ----
+#pragma unroll 1
+			for (int c0 = 0; c0 < N; c0 += 64) {
+				unsigned int v[64];
+				unsigned int *blk = col_t + c0 * MID_THREADS;
+#pragma unroll
+				for (int k = 0; k < 64; k++) v[k] = blk[k * MID_THREADS];
+				sort_network<64>(v);
+#pragma unroll
+				for (int k = 0; k < 64; k++) blk[k * MID_THREADS] = v[k];
+			}
+			// ---- 4. bitonic merges: runs of L = 64, then (NPAD = 256) L = 128 ----
+#pragma unroll 1
+			for (int L = 64; L < NPAD; L <<= 1) {
+				// first stage: element k of the lower run against element L-1-k of the upper run
+				const int log_l = L == 64 ? 6 : 7;
+#pragma unroll 2
+				for (int j = 0; j < NPAD / 2; j++) {
+					const int blk = j >> log_l, k = j & (L - 1);
+					unsigned int *lo = col_t + (blk * 2 * L + k) * MID_THREADS;
+					unsigned int *hi = col_t + (blk * 2 * L + 2 * L - 1 - k) * MID_THREADS;
+					const unsigned int x = *lo, y = *hi;
+					*lo = __vminu2(x, y);
+					*hi = __vmaxu2(x, y);
+				}
+				// half-cleaners down to blocks of 64 (only L = 128 has one: distance 64)
+#pragma unroll 1
+				for (int d = L >> 1; d >= 64; d >>= 1) {
+#pragma unroll 2
+					for (int j = 0; j < NPAD / 2; j++) {
+						const int blk = j >> 6, k = j & 63;	// (d == 64: the only half-cleaner distance above a block)
+						unsigned int *lo = col_t + (blk * 2 * d + k) * MID_THREADS;
+						unsigned int *hi = lo + d * MID_THREADS;
+						const unsigned int x = *lo, y = *hi;
+						*lo = __vminu2(x, y);
+						*hi = __vmaxu2(x, y);
+					}
+				}
+				// the last six stages of every 64-element block, in registers
+#pragma unroll 1
+				for (int c0 = 0; c0 < NPAD; c0 += 64) {
+					unsigned int v[64];
+					unsigned int *blk = col_t + c0 * MID_THREADS;
+#pragma unroll
+					for (int k = 0; k < 64; k++) v[k] = blk[k * MID_THREADS];
+					bitonic_merge_64(v);
+#pragma unroll
+					for (int k = 0; k < 64; k++) blk[k * MID_THREADS] = v[k];
+				}
+			}
+		}
+
+		// ---- 5. per-pixel tail on the sorted column ----
+		unsigned int res[2];
+		const unsigned long long S[2] = {Sa, Sb}, Q[2] = {Qa, Qb};
+#pragma unroll 1
+		for (int h = 0; h < 2; h++) {
+			Column c{reinterpret_cast<WORD *>(col) + 2 * tid + h, 2 * MID_THREADS};
+			if (is_median) {			// stacking.c:765-767, double -> WORD truncation
+				res[h] = (c.get((N - 1) >> 1) + c.get(N >> 1)) >> 1;
+			} else {
+				RejectState st{0, 0, 0, 0};
+				res[h] = reject_sorted_and_mean<false>(c, N, p.rejection, p.sig_low, p.sig_high, S[h], Q[h], st, nullptr, &p.fit);
+				if (active) {
+					if (st.rej_lo) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) st.rej_lo);
+					if (st.rej_hi) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) st.rej_hi);
+					if (st.guard) atomicAdd(&blk_counters[6], 1ull);
+					if (st.cap) atomicAdd(&blk_counters[7], 1ull);
+				}
+			}
+		}
+		if (active) *reinterpret_cast<unsigned int *>(p.out + out_idx) = res[0] | (res[1] << 16);
+	}
+	__syncthreads();
+	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
+		atomicAdd(&p.counters[tid], blk_counters[tid]);
+}
+
+// Same conditions as the 64-frame register kernel (ssc_stack_fast.cu), for 65..256 frames.
+bool mid_path_eligible(const StackParams &p, int is_median) {
+	const ssc_band &b = p.band;
+	if (b.n_frames <= 64 || b.n_frames > 256) return false;
+	if (!is_median && (b.shiftx || b.shifty)) return false;
+	// the linear fit's per-pixel loops dominate there and run better one pixel per thread (measured)
+	if (!is_median && p.rejection == LINEARFIT) return false;
+	if ((b.width & 1) || (b.frame_stride & 1) || (b.layer_stride & 1)) return false;
+	if (((uintptr_t) b.frames & 3) || ((uintptr_t) p.out & 3) || (p.out_layer_stride & 1)) return false;
+	if ((size_t) b.layers * p.out_layer_stride >= 0xFFFFFFF0ull) return false;	// 32-bit result indices
+	if ((unsigned long long) b.layers * b.out_rows * b.width >= 0xFFFFFFF0ull) return false;
+	if ((unsigned long long) b.frame_stride * sizeof(WORD) >= 0xFFFFFFF0ull) return false;	// 32-bit frame stride in bytes
+	return true;
+}
+
+template <int NPAD>
+static int launch_mid(const StackParams &p, int is_median, cudaStream_t stream) {
+	const ssc_band &b = p.band;
+	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * (b.width >> 1);
+	if (total == 0) return SSC_OK;
+	const size_t smem = (size_t) NPAD * MID_THREADS * sizeof(unsigned int);
+	if (cudaFuncSetAttribute(k_stack_mid<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
+		return SSC_ERR_CUDA;
+	const unsigned long long tiles = (total + MID_THREADS - 1) / MID_THREADS;
+	int dev = 0, sms = 148, per_sm = 1;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stack_mid<NPAD>, MID_THREADS, smem) != cudaSuccess || per_sm < 1)
+		per_sm = 1;
+	unsigned long long blocks = (unsigned long long) sms * per_sm * 4;	// looping blocks, a few per resident slot
+	if (blocks > tiles) blocks = tiles;
+	k_stack_mid<NPAD><<<(unsigned int) blocks, MID_THREADS, smem, stream>>>(p, (unsigned int) tiles, is_median);
+	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
+}
+
+int launch_stack_mid(const StackParams &p, int is_median, cudaStream_t stream) {
+	return p.band.n_frames <= 128 ? launch_mid<128>(p, is_median, stream) : launch_mid<256>(p, is_median, stream);
+}
+
+}  // namespace ssc

@@ -315,6 +315,56 @@ def test_register_network_kernel_equals_general_kernel(gpu, port, rej, n, norm):
         assert a.guard_fired == same["guard_fired"]
 
 
+@pytest.mark.parametrize("rej", list(REJ) + ["median"])
+@pytest.mark.parametrize("n,norm", [(65, 2), (100, 3), (128, 0), (129, 4), (200, 3), (256, 1)])
+def test_mid_kernel_equals_general_kernel(gpu, port, rej, n, norm):
+    """ssc_stack_mid.cu (65..256 frames: register network on runs of 64 + shared-memory bitonic merges)
+    against the general kernel and the oracle: same image, counters and guard events."""
+    fr = synth.make_frames(n, 1, 12, 48, seed=n + norm, outlier_p=8e-3, zero_p=2e-3, stars=2)
+    outs = []
+    for path in (0, 1):                                      # automatic (mid kernel), general kernel
+        gpu.set_kernel_path(path)
+        try:
+            if rej == "median":
+                res = gpu.stack_median(gpu.Sequence(fr), normalize=norm, want_coeff=True)
+            else:
+                rj, sig = REJ[rej]
+                res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), rj, sig, norm)
+        finally:
+            gpu.set_kernel_path(0)
+        outs.append(res)
+    a, b = outs
+    assert np.array_equal(a.data, b.data)
+    assert np.array_equal(a.irej, b.irej) and a.guard_fired == b.guard_fired and a.cap_hit == b.cap_hit
+    if rej == "median":
+        assert np.array_equal(a.data, port.stack_median(fr, normalize=norm, coeff=a.coeff)["out"])
+    else:
+        rj, sig = REJ[rej]
+        same = port.stack_mean(fr, rj, sig, norm, coeff=a.coeff, sd_mode=port.SD_EXACT)
+        assert np.array_equal(a.data, same["out"]) and np.array_equal(a.irej, same["irej"])
+        assert a.guard_fired == same["guard_fired"]
+
+
+def test_mid_kernel_rgb_ser_and_fallbacks(gpu, port):
+    """RGB + SER row order on the mid kernel; an odd width and registration shifts must fall back to the
+    general kernel and still agree with the oracle."""
+    fr = synth.make_frames(80, 3, 10, 32, seed=5, outlier_p=6e-3, zero_p=1e-3, stars=2)
+    for ro in (0, 1):
+        res = gpu.stack_mean_with_rejection(gpu.Sequence(fr, row_order=ro), 4, (4.0, 3.0), 3)
+        same = port.stack_mean(fr, 4, (4.0, 3.0), 3, coeff=res.coeff, row_order=ro, sd_mode=port.SD_EXACT)
+        assert np.array_equal(res.data, same["out"]) and np.array_equal(res.irej, same["irej"]), ro
+    fr = synth.make_frames(70, 1, 9, 31, seed=6, outlier_p=6e-3)            # odd width
+    res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), 2, (4.0, 3.0), 0)
+    same = port.stack_mean(fr, 2, (4.0, 3.0), 0, sd_mode=port.SD_EXACT)
+    assert np.array_equal(res.data, same["out"]) and np.array_equal(res.irej, same["irej"])
+    fr = synth.make_frames(70, 1, 12, 32, seed=7, outlier_p=6e-3)
+    sx = [(i * 7) % 5 - 2 for i in range(70)]
+    sy = [(i * 3) % 5 - 2 for i in range(70)]
+    res = gpu.stack_mean_with_rejection(gpu.Sequence(fr, shiftx=sx, shifty=sy), 2, (4.0, 3.0), 0)
+    same = port.stack_mean(fr, 2, (4.0, 3.0), 0, shiftx=sx, shifty=sy, sd_mode=port.SD_EXACT)
+    assert np.array_equal(res.data, same["out"]) and np.array_equal(res.irej, same["irej"])
+
+
 def test_fast_normalization_domain_fallback(gpu, port):
     """Coefficients outside the domain of the 2^52 conversion tricks (a nearly black frame against a
     bright reference: mul ~ 5e4, products beyond 2^31) take the conversion-based normalization."""
