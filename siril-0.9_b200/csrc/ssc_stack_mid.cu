@@ -1,5 +1,5 @@
-// ssc_stack_mid.cu -- K2/K3 for stacks of 65..256 frames without registration shifts (the deep-sky
-// shape of BASELINE.json's cfg4: 200 frames, winsorized rejection).
+// ssc_stack_mid.cu -- K2/K3 for stacks of 65..1024 frames without registration shifts (the shapes of
+// BASELINE.json's cfg4: 200 frames, winsorized rejection, and cfg5: 1000 frames, linear fit).
 //
 // The same two-pixels-per-thread packed u16x2 columns as ssc_stack_fast.cu, but a column no longer fits
 // the register file, so it lives in shared memory (col[i][thread], conflict-free) and is sorted in pieces:
@@ -11,7 +11,9 @@
 //      over shared memory (the partner of element k of one run is element L-1-k of the other), the last
 //      six stages of every 64-element block run in registers again (192 compare-exchanges);
 //   5. the sorted column goes through the same per-pixel rejection code as the general kernel
-//      (ssc_column.cuh), one pixel of the pair after the other.
+//      (ssc_column.cuh).  The block has twice as many threads as pixel pairs: the second half idles at a
+//      barrier through 1-4 and takes the second pixel of every pair here, so the serial per-pixel loops
+//      (winsorization, linear fit) run one pixel per thread.
 // Per pixel this is ~9 k instructions against ~50 k for the general kernel's shared-memory bitonic sort.
 #include "ssc_column.cuh"
 #include "ssc_kernels.h"
@@ -19,7 +21,6 @@
 
 namespace ssc {
 
-constexpr int MID_THREADS = 64;
 
 // the last six stages of a bitonic merge: v[0..64) bitonic -> ascending
 __device__ __forceinline__ void bitonic_merge_64(unsigned int (&v)[64]) {
@@ -36,7 +37,7 @@ __device__ __forceinline__ void bitonic_merge_64(unsigned int (&v)[64]) {
 	}
 }
 
-template <int KIND>
+template <int KIND, int MID_THREADS, int NPAD>
 __device__ __forceinline__ void normalize_column(unsigned int *col_t, const double *s_coef, int N,
 		unsigned int &Sa, unsigned int &Sb, unsigned long long &Qa, unsigned long long &Qb) {
 #pragma unroll 1
@@ -48,8 +49,8 @@ __device__ __forceinline__ void normalize_column(unsigned int *col_t, const doub
 			w[j] = col_t[(f0 + j) * MID_THREADS];
 			off[j] = 0.0; mul[j] = 1.0; sc[j] = 1.0;
 			if constexpr (KIND == ADDITIVE || KIND == ADDITIVE_SCALING) off[j] = s_coef[f0 + j];
-			if constexpr (KIND == MULTIPLICATIVE || KIND == MULTIPLICATIVE_SCALING) mul[j] = s_coef[256 + f0 + j];
-			if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) sc[j] = s_coef[512 + f0 + j];
+			if constexpr (KIND == MULTIPLICATIVE || KIND == MULTIPLICATIVE_SCALING) mul[j] = s_coef[NPAD + f0 + j];
+			if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) sc[j] = s_coef[2 * NPAD + f0 + j];
 		}
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
@@ -68,29 +69,34 @@ __device__ __forceinline__ void normalize_column(unsigned int *col_t, const doub
 	}
 }
 
-// NPAD: 128 or 256, the column length the merges work on (sentinels 0xFFFF behind the N samples)
-template <int NPAD>
-__global__ void __launch_bounds__(MID_THREADS)
+// NPAD: 128 .. 1024, the column length the merges work on (sentinels 0xFFFF behind the N samples);
+// MID_THREADS: pixel pairs per block (the block has 2 * MID_THREADS threads, see 5. above)
+template <int NPAD, int MID_THREADS>
+__global__ void __launch_bounds__(2 * MID_THREADS)
 k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 	extern __shared__ unsigned int col[];			// [NPAD][MID_THREADS] packed columns
-	__shared__ double s_coef[3 * 256];			// offset, mul, scale
+	__shared__ double s_coef[3 * NPAD];			// offset, mul, scale
 	__shared__ int s_fast_norm;
 	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
+	__shared__ unsigned long long s_S[2 * MID_THREADS], s_Q[2 * MID_THREADS];	// per pixel: [h * MID_THREADS + pair]
+	__shared__ unsigned int s_out[MID_THREADS];		// per pair: result index, bit 31 = inactive
+	__shared__ unsigned char s_layer[MID_THREADS];
 
 	const ssc_band &b = p.band;
 	const int W = b.width, W2 = W >> 1, N = b.n_frames, tid = threadIdx.x;
+	const bool sorter = tid < MID_THREADS;
 	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
 	const bool need_sort = is_median || p.rejection != NO_REJEC;
 
 	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
 	if (tid == 0) s_fast_norm = 1;
 	__syncthreads();
-	for (int f = tid; f < 256; f += MID_THREADS) {
+	for (int f = tid; f < NPAD; f += 2 * MID_THREADS) {
 		const bool have = norm && f < N;
 		const double off = have ? p.coeff[f] : 0.0, mul = have ? p.coeff[N + f] : 1.0, sc = have ? p.coeff[2 * N + f] : 1.0;
 		s_coef[f] = off;
-		s_coef[256 + f] = mul;
-		s_coef[512 + f] = sc;
+		s_coef[NPAD + f] = mul;
+		s_coef[2 * NPAD + f] = sc;
 		if (have) {	// domain of the 2^52 tricks (ssc_network.cuh): every intermediate stays below 2^31
 			const bool additive = p.normalize == ADDITIVE || p.normalize == ADDITIVE_SCALING;
 			const double bound = additive ? dadd(dmul(fabs(sc), 65535.0), fabs(off)) : dmul(dmul(fabs(sc), 65535.0), fabs(mul));
@@ -100,11 +106,12 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 	__syncthreads();
 
 	const unsigned int total = (unsigned int) ((unsigned long long) b.layers * b.out_rows * W2);	// < 2^32: mid_path_eligible
-	unsigned int *col_t = col + tid;
+	unsigned int *col_t = col + (tid & (MID_THREADS - 1));
 	const unsigned int sbase = (unsigned int) __cvta_generic_to_shared(col_t);
 	const unsigned int fstride32 = (unsigned int) (b.frame_stride * sizeof(WORD));
 
 	for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		if (sorter) {
 		unsigned int g = tile * MID_THREADS + tid;
 		const bool active = g < total;
 		if (!active) g = total - 1;
@@ -134,8 +141,8 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 		if (norm && !s_fast_norm) {
 			for (int f = 0; f < N; f++) {
 				const unsigned int w = col_t[f * MID_THREADS];
-				const unsigned int pa = normalize_sample(w & 0xFFFFu, p.normalize, s_coef[f], s_coef[256 + f], s_coef[512 + f]);
-				const unsigned int pb = normalize_sample(w >> 16, p.normalize, s_coef[f], s_coef[256 + f], s_coef[512 + f]);
+				const unsigned int pa = normalize_sample(w & 0xFFFFu, p.normalize, s_coef[f], s_coef[NPAD + f], s_coef[2 * NPAD + f]);
+				const unsigned int pb = normalize_sample(w >> 16, p.normalize, s_coef[f], s_coef[NPAD + f], s_coef[2 * NPAD + f]);
 				col_t[f * MID_THREADS] = pa | (pb << 16);
 				Sa += pa; Sb += pb;
 				Qa += (unsigned long long) pa * pa;
@@ -143,13 +150,17 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 			}
 		} else {
 			switch (norm ? p.normalize : NO_NORM) {
-			case NO_NORM: normalize_column<NO_NORM>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
-			case ADDITIVE: normalize_column<ADDITIVE>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
-			case MULTIPLICATIVE: normalize_column<MULTIPLICATIVE>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
-			case ADDITIVE_SCALING: normalize_column<ADDITIVE_SCALING>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
-			default: normalize_column<MULTIPLICATIVE_SCALING>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case NO_NORM: normalize_column<NO_NORM, MID_THREADS, NPAD>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case ADDITIVE: normalize_column<ADDITIVE, MID_THREADS, NPAD>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case MULTIPLICATIVE: normalize_column<MULTIPLICATIVE, MID_THREADS, NPAD>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case ADDITIVE_SCALING: normalize_column<ADDITIVE_SCALING, MID_THREADS, NPAD>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
+			default: normalize_column<MULTIPLICATIVE_SCALING, MID_THREADS, NPAD>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
 			}
 		}
+		s_S[tid] = Sa; s_S[MID_THREADS + tid] = Sb;
+		s_Q[tid] = Qa; s_Q[MID_THREADS + tid] = Qb;
+		s_out[tid] = out_idx | (active ? 0u : 0x80000000u);
+		s_layer[tid] = (unsigned char) layer;
 
 		if (need_sort) {
 			// ---- 3. runs of 64 through the register network ----
@@ -163,11 +174,11 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 #pragma unroll
 				for (int k = 0; k < 64; k++) blk[k * MID_THREADS] = v[k];
 			}
-			// ---- 4. bitonic merges: runs of L = 64, then (NPAD = 256) L = 128 ----
+			// ---- 4. bitonic merges of runs of L = 64, 128, ... NPAD / 2 ----
+			int log_l = 6;
 #pragma unroll 1
-			for (int L = 64; L < NPAD; L <<= 1) {
+			for (int L = 64; L < NPAD; L <<= 1, log_l++) {
 				// first stage: element k of the lower run against element L-1-k of the upper run
-				const int log_l = L == 64 ? 6 : 7;
 #pragma unroll 2
 				for (int j = 0; j < NPAD / 2; j++) {
 					const int blk = j >> log_l, k = j & (L - 1);
@@ -177,12 +188,13 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 					*lo = __vminu2(x, y);
 					*hi = __vmaxu2(x, y);
 				}
-				// half-cleaners down to blocks of 64 (only L = 128 has one: distance 64)
+				// half-cleaners at distances L/2 ... 64
+				int log_d = log_l - 1;
 #pragma unroll 1
-				for (int d = L >> 1; d >= 64; d >>= 1) {
+				for (int d = L >> 1; d >= 64; d >>= 1, log_d--) {
 #pragma unroll 2
 					for (int j = 0; j < NPAD / 2; j++) {
-						const int blk = j >> 6, k = j & 63;	// (d == 64: the only half-cleaner distance above a block)
+						const int blk = j >> log_d, k = j & (d - 1);
 						unsigned int *lo = col_t + (blk * 2 * d + k) * MID_THREADS;
 						unsigned int *hi = lo + d * MID_THREADS;
 						const unsigned int x = *lo, y = *hi;
@@ -203,18 +215,22 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 				}
 			}
 		}
+		}	// sorter
+		__syncthreads();
 
-		// ---- 5. per-pixel tail on the sorted column ----
-		unsigned int res[2];
-		const unsigned long long S[2] = {Sa, Sb}, Q[2] = {Qa, Qb};
-#pragma unroll 1
-		for (int h = 0; h < 2; h++) {
-			Column c{reinterpret_cast<WORD *>(col) + 2 * tid + h, 2 * MID_THREADS};
+		// ---- 5. per-pixel tail on the sorted column: thread t takes pixel t / MID_THREADS of pair t % MID_THREADS ----
+		{
+			const int pair = tid & (MID_THREADS - 1), h = tid / MID_THREADS;
+			const unsigned int oi = s_out[pair];
+			const bool active = !(oi & 0x80000000u);
+			const int layer = s_layer[pair];
+			Column c{reinterpret_cast<WORD *>(col) + 2 * pair + h, 2 * MID_THREADS};
+			unsigned int res;
 			if (is_median) {			// stacking.c:765-767, double -> WORD truncation
-				res[h] = (c.get((N - 1) >> 1) + c.get(N >> 1)) >> 1;
+				res = (c.get((N - 1) >> 1) + c.get(N >> 1)) >> 1;
 			} else {
 				RejectState st{0, 0, 0, 0};
-				res[h] = reject_sorted_and_mean<false>(c, N, p.rejection, p.sig_low, p.sig_high, S[h], Q[h], st, nullptr, &p.fit);
+				res = reject_sorted_and_mean<false>(c, N, p.rejection, p.sig_low, p.sig_high, s_S[tid], s_Q[tid], st, nullptr, &p.fit);
 				if (active) {
 					if (st.rej_lo) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) st.rej_lo);
 					if (st.rej_hi) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) st.rej_hi);
@@ -222,51 +238,54 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 					if (st.cap) atomicAdd(&blk_counters[7], 1ull);
 				}
 			}
+			if (active) p.out[(oi & 0x7FFFFFFFu) + h] = (WORD) res;
 		}
-		if (active) *reinterpret_cast<unsigned int *>(p.out + out_idx) = res[0] | (res[1] << 16);
+		__syncthreads();	// the columns are overwritten by the next tile
 	}
-	__syncthreads();
 	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
 		atomicAdd(&p.counters[tid], blk_counters[tid]);
 }
 
-// Same conditions as the 64-frame register kernel (ssc_stack_fast.cu), for 65..256 frames.
+// Same conditions as the 64-frame register kernel (ssc_stack_fast.cu), for 65..1024 frames.
 bool mid_path_eligible(const StackParams &p, int is_median) {
 	const ssc_band &b = p.band;
-	if (b.n_frames <= 64 || b.n_frames > 256) return false;
+	if (b.n_frames <= 64 || b.n_frames > 1024) return false;
 	if (!is_median && (b.shiftx || b.shifty)) return false;
-	// the linear fit's per-pixel loops dominate there and run better one pixel per thread (measured)
-	if (!is_median && p.rejection == LINEARFIT) return false;
 	if ((b.width & 1) || (b.frame_stride & 1) || (b.layer_stride & 1)) return false;
 	if (((uintptr_t) b.frames & 3) || ((uintptr_t) p.out & 3) || (p.out_layer_stride & 1)) return false;
-	if ((size_t) b.layers * p.out_layer_stride >= 0xFFFFFFF0ull) return false;	// 32-bit result indices
+	if ((size_t) b.layers * p.out_layer_stride >= 0x7FFFFFF0ull) return false;	// 31-bit result indices
 	if ((unsigned long long) b.layers * b.out_rows * b.width >= 0xFFFFFFF0ull) return false;
 	if ((unsigned long long) b.frame_stride * sizeof(WORD) >= 0xFFFFFFF0ull) return false;	// 32-bit frame stride in bytes
 	return true;
 }
 
-template <int NPAD>
+template <int NPAD, int MID_THREADS>
 static int launch_mid(const StackParams &p, int is_median, cudaStream_t stream) {
 	const ssc_band &b = p.band;
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * (b.width >> 1);
 	if (total == 0) return SSC_OK;
 	const size_t smem = (size_t) NPAD * MID_THREADS * sizeof(unsigned int);
-	if (cudaFuncSetAttribute(k_stack_mid<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
+	if (cudaFuncSetAttribute(k_stack_mid<NPAD, MID_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
 	const unsigned long long tiles = (total + MID_THREADS - 1) / MID_THREADS;
 	int dev = 0, sms = 148, per_sm = 1;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stack_mid<NPAD>, MID_THREADS, smem) != cudaSuccess || per_sm < 1)
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stack_mid<NPAD, MID_THREADS>, 2 * MID_THREADS, smem) != cudaSuccess || per_sm < 1)
 		per_sm = 1;
 	unsigned long long blocks = (unsigned long long) sms * per_sm * 4;	// looping blocks, a few per resident slot
 	if (blocks > tiles) blocks = tiles;
-	k_stack_mid<NPAD><<<(unsigned int) blocks, MID_THREADS, smem, stream>>>(p, (unsigned int) tiles, is_median);
+	k_stack_mid<NPAD, MID_THREADS><<<(unsigned int) blocks, 2 * MID_THREADS, smem, stream>>>(p, (unsigned int) tiles, is_median);
 	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
 }
 
+// columns of 64 KB per block: 64 pixel pairs up to 256 frames, 32 up to 512, 16 up to 1024
 int launch_stack_mid(const StackParams &p, int is_median, cudaStream_t stream) {
-	return p.band.n_frames <= 128 ? launch_mid<128>(p, is_median, stream) : launch_mid<256>(p, is_median, stream);
+	const int n = p.band.n_frames;
+	if (n <= 128) return launch_mid<128, 64>(p, is_median, stream);
+	if (n <= 256) return launch_mid<256, 64>(p, is_median, stream);
+	if (n <= 512) return launch_mid<512, 32>(p, is_median, stream);
+	return launch_mid<1024, 16>(p, is_median, stream);
 }
 
 }  // namespace ssc

@@ -316,11 +316,13 @@ def test_register_network_kernel_equals_general_kernel(gpu, port, rej, n, norm):
 
 
 @pytest.mark.parametrize("rej", list(REJ) + ["median"])
-@pytest.mark.parametrize("n,norm", [(65, 2), (100, 3), (128, 0), (129, 4), (200, 3), (256, 1)])
+@pytest.mark.parametrize("n,norm", [(65, 2), (100, 3), (128, 0), (129, 4), (200, 3), (256, 1), (257, 2), (500, 3),
+                                    (512, 0), (700, 4), (1024, 1)])
 def test_mid_kernel_equals_general_kernel(gpu, port, rej, n, norm):
-    """ssc_stack_mid.cu (65..256 frames: register network on runs of 64 + shared-memory bitonic merges)
+    """ssc_stack_mid.cu (65..1024 frames: register network on runs of 64 + shared-memory bitonic merges)
     against the general kernel and the oracle: same image, counters and guard events."""
-    fr = synth.make_frames(n, 1, 12, 48, seed=n + norm, outlier_p=8e-3, zero_p=2e-3, stars=2)
+    h, w = (12, 48) if n <= 256 else (6, 40)
+    fr = synth.make_frames(n, 1, h, w, seed=n + norm, outlier_p=8e-3, zero_p=2e-3, stars=2)
     outs = []
     for path in (0, 1):                                      # automatic (mid kernel), general kernel
         gpu.set_kernel_path(path)
