@@ -174,13 +174,32 @@ def reference_arm(args, pkg, torch):
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=desc),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def _emit(line):
+    """The ONE JSON line, on the real stdout (see main: everything else on fd 1 went to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    # Libraries write to stdout behind our back (NCCL prints its version line there, the reference's
+    # stackers printf their block layout): keep fd 1 for the JSON line alone, send the rest to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -386,7 +405,7 @@ def main():
                      matches_device_path=e2e_parity),
             gpu_launches=launches_per_step * args.steps,
             clocks=clocks, parity=parity, cpu_baseline=cpu)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -13,17 +13,9 @@ __device__ __forceinline__ double word_to_double(unsigned int p) {
 // round_to_WORD (utils.c:68-74) for |y| < 2^31: floor(y + 0.5) read from the low word of
 // (y + 0.5) +rz 1.5*2^52, then max(min(., 65535), 0).  Equals the reference for every such y:
 // y <= 0 -> floor <= 0 -> 0;  0 < y <= 65535 -> trunc(y + 0.5);  y > 65535 -> >= 65535 -> 65535.
-#ifndef SSC_NORM_XU_OUT
-#define SSC_NORM_XU_OUT 0
-#endif
 __device__ __forceinline__ unsigned int round_to_word_fast(double y) {
-#if SSC_NORM_XU_OUT
-	// F2I.F64.TRUNC saturates and maps NaN to 0: valid for every y, costs a conversion-unit slot
-	return (unsigned int) __vimin_s32_relu(__double2int_rz(dadd(y, 0.5)), 65535);
-#else
 	double u = __dadd_rz(dadd(y, 0.5), 6755399441055744.0);
 	return (unsigned int) __vimin_s32_relu(__double2loint(u), 65535);
-#endif
 }
 
 template <int NP>
@@ -41,11 +33,7 @@ template <int KIND>
 __device__ __forceinline__ unsigned int normalize_pair_fast(unsigned int w, double off, double mul, double sc,
 		unsigned long long &Qa, unsigned long long &Qb) {
 	// I2F.F64.U16 reads either half of the packed word directly (conversion unit, off the ALU pipe)
-#ifdef SSC_NORM_MAGIC_IN
-	double da = word_to_double(w & 0xFFFFu), db = word_to_double(w >> 16);
-#else
 	double da = (double) (unsigned short) (w & 0xFFFFu), db = (double) (unsigned short) (w >> 16);
-#endif
 	if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) {
 		da = dmul(da, sc);
 		db = dmul(db, sc);

@@ -43,9 +43,6 @@ __device__ __forceinline__ void normalize_all(unsigned int (&v)[NP], int N, cons
 	}
 }
 
-#ifndef SSC_SIGMA_REG_PASSES
-#define SSC_SIGMA_REG_PASSES 4	// clipping passes unrolled in registers before a pixel goes to the leftover list
-#endif
 enum { MODE_MEDIAN = 0, MODE_NOREJ = 1, MODE_SIGMA_REG = 2, MODE_QUEUE = 3 };
 
 // MODE_SIGMA_REG stages the band through shared memory so that everything before the sorting
@@ -119,25 +116,15 @@ __device__ __forceinline__ bool clip_cannot_fire(unsigned long long S, unsigned 
 	return (d_lo == 0 || (float) d_lo < t_lo) && (d_hi == 0 || (float) d_hi < t_hi);
 }
 
-#ifndef SSC_STAGE_ROUNDS
-#define SSC_STAGE_ROUNDS 1
-#endif
-#ifndef SSC_FAST_CTAS
-#define SSC_FAST_CTAS 4
-#endif
-constexpr int FAST_STAGE_ROUNDS = SSC_STAGE_ROUNDS;
 constexpr int FAST_QUEUE_WORDS = 12, FAST_QUEUE_CAP = 96;	// per warp: < 32 waiting + up to 64 new per tile
 
 // FULL: n_frames == NP (no sentinel padding, no per-frame bound checks in the unrolled code)
 // MODE: which tail follows the network (one per instantiation: the kernel is instruction-fetch
 //       sensitive, dead alternatives are not carried along)
-#ifndef SSC_FAST_THREADS
-#define SSC_FAST_THREADS 128
-#endif
-constexpr int FAST_THREADS = SSC_FAST_THREADS;
+constexpr int FAST_THREADS = 128;	// 4 blocks per SM (measured: 256/512-thread blocks, tile barriers and warp ping-pong are no faster)
 
 template <int NP, bool FULL, int MODE>
-__global__ void __launch_bounds__(FAST_THREADS, MODE == MODE_SIGMA_REG ? SSC_FAST_CTAS : 512 / FAST_THREADS)
+__global__ void __launch_bounds__(FAST_THREADS, 4)
 k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	extern __shared__ unsigned int cols[];		// [NP][FAST_THREADS] packed columns
 	__shared__ double s_coef[3 * 64];
@@ -164,7 +151,7 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	// MODE_SIGMA_REG: the dynamic shared memory holds the per-warp queues of pixels whose clipping
 	// has to be evaluated exactly, [warp][FAST_QUEUE_WORDS][FAST_QUEUE_CAP]
 	// behind the staging buffer [NP][FAST_THREADS] (see normalize_staged)
-	unsigned int (*queue)[FAST_QUEUE_CAP] = reinterpret_cast<unsigned int (*)[FAST_QUEUE_CAP]>(cols + NP / FAST_STAGE_ROUNDS * FAST_THREADS)
+	unsigned int (*queue)[FAST_QUEUE_CAP] = reinterpret_cast<unsigned int (*)[FAST_QUEUE_CAP]>(cols + NP * FAST_THREADS)
 			+ (tid >> 5) * FAST_QUEUE_WORDS;
 	int qcount = 0;		// items on this warp's queue (warp-uniform)
 	unsigned int lane_rej[6] = {0, 0, 0, 0, 0, 0};	// this lane's share of irej[3][2] (MODE_SIGMA_REG)
@@ -192,11 +179,6 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	__syncthreads();
 
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * W2;
-#ifdef SSC_PINGPONG
-	static_assert(FAST_THREADS == 256, "ping-pong pairs warps w and w + 4");
-	if (MODE == MODE_SIGMA_REG && ((tid >> 7) & 1) && blockIdx.x < n_tiles && !(norm && !s_fast_norm))
-		asm volatile("bar.arrive %0, 64;" :: "r"(1 + 2 * ((tid >> 5) & 3)) : "memory");	// the first warp of each pair starts
-#endif
 	// MODE_SIGMA_REG: request a tile's samples (see the gather below); pf_* describe the requested tile
 	int pf_layer = 0;
 	unsigned int pf_out_idx = 0;
@@ -235,9 +217,6 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	for (unsigned long long tile = blockIdx.x; ; tile += gridDim.x) {
 	const bool more = tile < n_tiles;
 	if (MODE != MODE_SIGMA_REG && !more) break;
-#ifdef SSC_TILE_SYNC
-	if (MODE == MODE_SIGMA_REG) __syncthreads();
-#endif
 	if (more) {
 	unsigned long long g = tile * FAST_THREADS + tid;
 	const bool active = g < total;
@@ -391,21 +370,7 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 			// candidate window (a third low, a sixth high) goes to the leftover list.  With NP >= 32
 			// and at most 7 rejections the reference's "N - r <= 4" break (:1684) cannot be reached.
 			static_assert(FULL && NP >= 32 && (NP & (NP - 1)) == 0, "needs a full stack of 32 or 64 frames");
-#ifdef SSC_PINGPONG
-			// Ping-pong: warps w and w + 4 share a scheduler; only one of them runs the (ALU-bound)
-			// network at a time, the other one meanwhile stages and normalizes its next tile on the
-			// FP64 / conversion / load-store pipes.  Two named barriers per pair hand the turn over.
-			{
-				const int pair = (tid >> 5) & 3, second = (tid >> 7) & 1;
-				asm volatile("bar.sync %0, 64;" :: "r"(1 + 2 * pair + second) : "memory");	// wait for my turn
-				sort_network<NP>(v);
-				const bool last = tile + gridDim.x >= n_tiles;	// (block-uniform) nobody waits for the very last hand-over
-				if (!(second && last))
-					asm volatile("bar.arrive %0, 64;" :: "r"(1 + 2 * pair + (second ^ 1)) : "memory");	// the partner's turn
-			}
-#else
 			sort_network<NP>(v);
-#endif
 			bool need[2];
 #pragma unroll
 			for (int h = 0; h < 2; h++) {
@@ -639,7 +604,7 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * (b.width >> 1);
 	if (total == 0) return SSC_OK;
 	const size_t smem = MODE == MODE_SIGMA_REG
-			? (size_t) (NP / FAST_STAGE_ROUNDS) * FAST_THREADS * sizeof(unsigned int)
+			? (size_t) NP * FAST_THREADS * sizeof(unsigned int)
 				+ (size_t) (FAST_THREADS / 32) * FAST_QUEUE_WORDS * FAST_QUEUE_CAP * sizeof(unsigned int)
 			: (size_t) NP * FAST_THREADS * sizeof(unsigned int);
 	if (cudaFuncSetAttribute(k_stack_fast<NP, FULL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)

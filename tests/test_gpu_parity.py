@@ -367,6 +367,31 @@ def test_mid_kernel_rgb_ser_and_fallbacks(gpu, port):
     assert np.array_equal(res.data, same["out"]) and np.array_equal(res.irej, same["irej"])
 
 
+@pytest.mark.parametrize("n", [32, 64])
+def test_sigma_register_kernel_hand_backs(gpu, port, n):
+    """The 32/64-frame sigma kernel keeps 3 low / 6 high candidates per pixel; pixels that reject more, and
+    whole launches whose coefficients leave the fast normalization's domain, are handed to the general
+    kernel through the index list.  Both must give the oracle's image and counters."""
+    rng = np.random.default_rng(n)
+    fr = rng.normal(3000, 30, size=(n, 1, 16, 64)).clip(0, 65535).astype(np.uint16)
+    hot = rng.random(fr.shape) < 0.12                       # ~8 bright outliers per 64-frame column
+    fr[hot] = rng.integers(20000, 60000, size=int(hot.sum())).astype(np.uint16)
+    fr[rng.random(fr.shape) < 0.04] = 0                     # and a few dead samples (low side)
+    for norm in (0, 2):
+        res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), 2, (4.0, 3.0), norm)
+        same = port.stack_mean(fr, 2, (4.0, 3.0), norm, coeff=res.coeff, sd_mode=port.SD_EXACT)
+        assert np.array_equal(res.data, same["out"]) and np.array_equal(res.irej, same["irej"]), norm
+        assert res.guard_fired == same["guard_fired"]
+        assert res.irej[0, 1] > 6 * 16 * 64 * 0.3             # many pixels did leave the 6-candidate window
+    fr2 = rng.normal(50000, 300, size=(n, 1, 16, 32)).clip(0, 65535).astype(np.uint16)
+    fr2[3] = rng.integers(1, 4, size=(1, 16, 32)).astype(np.uint16)     # location ~2: mul ~ 25000
+    fr2[3, 0, 2, :8] = 60000                                            # 60000 * 25000 > 2^31
+    for norm in (2, 3):
+        res = gpu.stack_mean_with_rejection(gpu.Sequence(fr2), 2, (4.0, 3.0), norm)
+        same = port.stack_mean(fr2, 2, (4.0, 3.0), norm, coeff=res.coeff, sd_mode=port.SD_EXACT)
+        assert np.array_equal(res.data, same["out"]) and np.array_equal(res.irej, same["irej"]), norm
+
+
 def test_fast_normalization_domain_fallback(gpu, port):
     """Coefficients outside the domain of the 2^52 conversion tricks (a nearly black frame against a
     bright reference: mul ~ 5e4, products beyond 2^31) take the conversion-based normalization."""
