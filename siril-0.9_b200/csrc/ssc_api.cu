@@ -373,6 +373,10 @@ int upload_piece(const Job &job, Dev &d, const Piece &pc, ssc_band &band) {
 int run_job(const Job &job) {
 	using clk = std::chrono::steady_clock;
 	const auto t_begin = clk::now();
+	static const bool trace = getenv("SSC_TRACE") != nullptr;	// phase timeline on stderr (debug aid)
+	auto mark = [&](const char *what) {
+		if (trace) fprintf(stderr, "[ssc trace] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(clk::now() - t_begin).count(), what);
+	};
 	const ssc_sequence_view &v = job.seq->view;
 	const int W = v.rx, H = v.ry, C = v.nb_layers, N = (int) job.images.size();
 	const size_t plane = (size_t) W * H;
@@ -398,7 +402,9 @@ int run_job(const Job &job) {
 		const int rows = H / G + (g < H % G ? 1 : 0);
 		CU(cudaSetDevice(d.id));
 		size_t free_b = 0, total_b = 0;
+		mark("before cudaMemGetInfo");
 		CU(cudaMemGetInfo(&free_b, &total_b));
+		mark("after cudaMemGetInfo");
 		{
 			auto it = g_cache.find(d.id);	// what this library already holds on the device is reusable
 			if (it != g_cache.end()) free_b += it->second.frames.cap + it->second.out.cap + it->second.hist.cap
@@ -433,6 +439,7 @@ int run_job(const Job &job) {
 		d.frames = (WORD *) dc.frames.p; d.out = (WORD *) dc.out.p;
 		d.counters = (unsigned long long *) dc.counters.p; d.coeff = (double *) dc.coeff.p;
 		CU(cudaMemsetAsync(d.counters, 0, SSC_COUNTERS * sizeof(unsigned long long), d.stream));
+		mark("buffers ensured");
 		if (job.op == OP_SUM) {
 			SSC_ENSURE(acc, (size_t) C * d.max_rows * W * sizeof(uint32_t));
 			SSC_ENSURE(maxim, sizeof(unsigned long long));
@@ -471,6 +478,7 @@ int run_job(const Job &job) {
 		}
 	}
 
+	mark("planned, workspace ready");
 	double t_h2d = 0, t_dev = 0, t_d2h = 0;
 	auto t_phase = clk::now();
 	auto phase_end = [&](double &acc_ms) -> int {	// sync all devices, book the wall time of this phase
@@ -490,6 +498,7 @@ int run_job(const Job &job) {
 
 	std::vector<ssc_band> bands(G);
 	int rc;
+	mark("setup synchronised");
 
 	// --- normalization statistics: K4 per band, combine, K5, K6 ---
 	std::vector<double> h_coeff((size_t) 3 * N);
@@ -561,6 +570,7 @@ int run_job(const Job &job) {
 	if (!result) return fail(SSC_ERR_GENERIC, "result allocation failed");
 	struct ResultGuard { WORD *&p; ~ResultGuard() { free(p); } } rguard{result};
 
+	mark("normalization done");
 	log_msg("Starting stacking...\n");
 	unsigned long long h_max = 0;
 	size_t max_pieces = 0;
@@ -676,6 +686,7 @@ int run_job(const Job &job) {
 		}
 	}
 
+	mark("stack + download done");
 	ssc_result res;
 	memset(&res, 0, sizeof(res));
 	for (auto &d : devs) {
@@ -726,6 +737,7 @@ int run_job(const Job &job) {
 		g_result = res;
 		g_has_result = true;
 	}
+	mark("result published");
 	return SSC_OK;
 }
 
