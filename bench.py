@@ -29,6 +29,11 @@ import time
 
 import numpy as np
 
+# DRAM bytes of one K3 launch over the whole benchmark image, measured once under ncu --set full
+# (9.237 GB read + 0.168 GB written; the algorithmic bytes are 9.360 GB)
+K3_DRAM_BYTES_N1 = 9_237_196_000 + 168_022_016
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -394,7 +399,9 @@ def main():
                         parallelism="row bands x%d" % world, l2="inputs (9.2 GB) exceed L2 (126 MB): no flush needed",
                         seed=hex(SEED), rejection_counters=irej.tolist(), guard_fired=guard, cap_hit=cap),
             roofline=dict(bound="hbm", kernel="k_stack_fast<64,true,SIGMA_REG> (K3: normalize + sigma-clip + mean, register sorting network)",
-                          achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                          achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=K3_DRAM_BYTES_N1 // world,
+                          traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of the "
+                                         "whole-image launch (profiles/r01_ncu_k_stack_fast_full_size_launch.txt), / ranks",
                           peak_source=peak_src, algorithmic_bytes_per_launch=bytes_stack,
                           ms_per_launch=ms_stack),
             step_breakdown_ms=dict(histogram_allreduce=ms_hist, ikss_coeffs=ms_ikss, stack=ms_stack,
