@@ -215,9 +215,11 @@ int launch_histogram(const ssc_band &b, uint32_t *hist, cudaStream_t stream) {
 constexpr int IKSS_THREADS = 1024;
 
 // terms of siril_stats_double_bwmv, statistics.c:136-145
-__device__ __forceinline__ void bwmv_term(double d, double m, double mad9, double &up, double &down) {
+// (the two divisions per bin -- by the histogram norm and by 9 MAD -- go through Reciprocal: the same
+// correctly rounded quotients from one real division per thread and IKSS iteration)
+__device__ __forceinline__ void bwmv_term(double d, double m, const Reciprocal &inv_mad9, double &up, double &down) {
 	double dm = dsub(d, m);
-	double yi = ddiv(dm, mad9);
+	double yi = inv_mad9.divide(dm);
 	double yi2 = dmul(yi, yi);
 	double ai = (fabs(yi) < 1.0) ? 1.0 : 0.0;
 	double omy = dsub(1.0, yi2);
@@ -290,25 +292,38 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 	const unsigned long long n_total = cum[65535];
 
 	for (int it = 0; it < SSC_ITER_CAP; it++) {
-		if (tid == 0) {
+		if (tid < 32) {
+			// Warp 0 finds the order statistics together: every search is a 33-ary search, 32 probes
+			// of the (global-memory) prefix counts per round instead of one -- the dependent loads
+			// were this kernel's critical path.  All lanes carry the same scalars; lane 0 publishes.
+			const int lane = tid;
 			const int bi = s_bi, bj = s_bj;
 			const unsigned long long base = cum[bi - 1];
 			const unsigned long long n = bj > bi ? (unsigned long long) cum[bj - 1] - base : 0ull;
-			s_n = n;
 			if (n < 1) {		// statistics.c:161-164
-				s_loc = s_scale = 0.0;
-				s_done = 1;
+				if (lane == 0) { s_n = n; s_loc = s_scale = 0.0; s_done = 1; }
 			} else {
+				// smallest k in [lo, hi] with pred(k), pred monotone and pred(hi) true
+				auto search = [&](int lo, int hi, auto pred) {
+					while (lo < hi) {
+						const int span = hi - lo, step = span / 32 + 1;
+						int pos = lo + (lane + 1) * step - 1;
+						if (pos > hi) pos = hi;
+						const unsigned int hit = __ballot_sync(0xffffffffu, pred(pos));
+						const int first = __ffs(hit) - 1;		// some lane sits on hi: hit != 0
+						const int p_first = __shfl_sync(0xffffffffu, pos, first);
+						const int p_prev = __shfl_sync(0xffffffffu, pos, first > 0 ? first - 1 : 0);
+						hi = p_first;
+						if (first > 0) lo = p_prev + 1;
+					}
+					return lo;
+				};
 				// median: bins holding ranks (n-1)/2 and n/2 (gsl_stats_median_from_sorted_data)
-				unsigned long long rk[2] = {(n - 1) >> 1, n >> 1};
+				const unsigned long long rk[2] = {(n - 1) >> 1, n >> 1};
 				int kb[2];
 				for (int q = 0; q < 2; q++) {
-					int lo = bi, hi = bj - 1;	// smallest k with cum[k] - base > rank
-					while (lo < hi) {
-						int mid = (lo + hi) >> 1;
-						if ((unsigned long long) cum[mid] - base > rk[q]) hi = mid; else lo = mid + 1;
-					}
-					kb[q] = lo;
+					const unsigned long long rank = rk[q];
+					kb[q] = search(bi, bj - 1, [&](int k) { return (unsigned long long) cum[k] - base > rank; });
 				}
 				double dl = ddiv((double) kb[0], norm), dr = ddiv((double) kb[1], norm);
 				double m = rk[0] == rk[1] ? dl : ddiv(dadd(dl, dr), 2.0);
@@ -317,27 +332,18 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 				// u_k = |2k - M2|; only the mirror pair (k, M2 - k) ties, and there the FP
 				// deltas decide.  C(u) = samples with u_k <= u, from the prefix counts.
 				const int M2 = kb[0] + kb[1];
+				auto count_within = [&](int u) -> unsigned long long {
+					int khi = (M2 + u) >> 1;			// floor((M2+u)/2)
+					int klo = M2 - u >= 0 ? (M2 - u + 1) >> 1 : 0;	// ceil((M2-u)/2)
+					if (khi > bj - 1) khi = bj - 1;
+					if (klo < bi) klo = bi;
+					return khi >= klo ? (unsigned long long) cum[khi] - cum[klo - 1] : 0ull;
+				};
 				double dv[2];
 				for (int q = 0; q < 2; q++) {
-					int ulo = 0, uhi = 2 * 65536;
-					while (ulo < uhi) {
-						int u = (ulo + uhi) >> 1;
-						int khi = (M2 + u) >> 1;			// floor((M2+u)/2)
-						int klo = M2 - u >= 0 ? (M2 - u + 1) >> 1 : 0;	// ceil((M2-u)/2)
-						if (khi > bj - 1) khi = bj - 1;
-						if (klo < bi) klo = bi;
-						unsigned long long cnt = khi >= klo ? (unsigned long long) cum[khi] - cum[klo - 1] : 0ull;
-						if (cnt > rk[q]) uhi = u; else ulo = u + 1;
-					}
-					const int u = ulo;
-					unsigned long long below = 0;	// C(u - 1)
-					if (u > 0) {
-						int khi = (M2 + u - 1) >> 1;
-						int klo = M2 - (u - 1) >= 0 ? (M2 - (u - 1) + 1) >> 1 : 0;
-						if (khi > bj - 1) khi = bj - 1;
-						if (klo < bi) klo = bi;
-						below = khi >= klo ? (unsigned long long) cum[khi] - cum[klo - 1] : 0ull;
-					}
+					const unsigned long long rank = rk[q];
+					const int u = search(0, 2 * 65536, [&](int uu) { return count_within(uu) > rank; });
+					const unsigned long long below = u > 0 ? count_within(u - 1) : 0ull;	// C(u - 1)
 					const int k1 = (M2 - u) >> 1, k2 = (M2 + u) >> 1;	// exact: u has M2's parity here
 					const bool in1 = (M2 - u) >= 0 && k1 >= bi && k1 < bj;
 					const bool in2 = k2 != k1 && k2 >= bi && k2 < bj;
@@ -353,8 +359,11 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 						dv[q] = pos < c2 ? d2 : d1;
 					}
 				}
-				s_m = m;
-				s_mad = rk[0] == rk[1] ? dv[0] : ddiv(dadd(dv[0], dv[1]), 2.0);
+				if (lane == 0) {
+					s_n = n;
+					s_m = m;
+					s_mad = rk[0] == rk[1] ? dv[0] : ddiv(dadd(dv[0], dv[1]), 2.0);
+				}
 			}
 		}
 		__syncthreads();
@@ -365,14 +374,14 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 		const int bi = s_bi, bj = s_bj;
 		double u = 0.0, w = 0.0;
 		if (mad > 0.0) {
-			const double mad9 = dmul(9.0, mad);
+			const Reciprocal inv_mad9(dmul(9.0, mad)), inv_norm(norm);
 			for (int k = 0; k < 64; k++) {
 				int bin = tid * 64 + k;
 				if (bin < bi || bin >= bj) continue;
 				uint32_t c = h[bin];
 				if (c == 0) continue;
 				double tu, tw;
-				bwmv_term(ddiv((double) bin, norm), m, mad9, tu, tw);
+				bwmv_term(inv_norm.divide((double) bin), m, inv_mad9, tu, tw);
 				u = dadd(u, dmul((double) c, tu));
 				w = dadd(w, dmul((double) c, tw));
 			}
