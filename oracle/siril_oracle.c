@@ -774,8 +774,10 @@ int so_ikss_hist(const uint32_t hist[65536], double norm, double *location, doub
 		if (mad > 0.0) {
 			for (c = 0; c < 1024; c++) {
 				double u = 0.0, w = 0.0, tu, tw;
-				for (k = c * 64; k < c * 64 + 64; k++) {
-					if (k < bi || k >= bj || hist[k] == 0)
+				/* partial sum c takes bins bi + c, bi + c + 1024, ... of the clipping window (the
+				 * order k_ikss uses: the window's bins spread evenly over its 1024 threads) */
+				for (k = bi + c; k < bj; k += 1024) {
+					if (hist[k] == 0)
 						continue;
 					bwmv_term((double) k / norm, m, mad, &tu, &tw);
 					u += (double) hist[k] * tu;

@@ -375,9 +375,9 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 		double u = 0.0, w = 0.0;
 		if (mad > 0.0) {
 			const Reciprocal inv_mad9(dmul(9.0, mad)), inv_norm(norm);
-			for (int k = 0; k < 64; k++) {
-				int bin = tid * 64 + k;
-				if (bin < bi || bin >= bj) continue;
+			// thread t takes bins bi + t, bi + t + 1024, ... of the clipping window: the window (a few
+			// hundred bins after the first iteration) is spread over all threads, loads coalesce
+			for (int bin = bi + tid; bin < bj; bin += IKSS_THREADS) {
 				uint32_t c = h[bin];
 				if (c == 0) continue;
 				double tu, tw;
