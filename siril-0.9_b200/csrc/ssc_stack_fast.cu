@@ -4,21 +4,35 @@
 //
 // One thread owns TWO horizontally adjacent pixels.  Their samples travel
 // packed as u16x2 in one 32-bit register per frame -- which is exactly how two
-// adjacent WORDs sit in memory, so a frame costs one coalesced 4-byte load per
+// adjacent WORDs sit in memory, so a frame costs one coalesced 4-byte access per
 // thread (128 B per warp) and no repacking.  The NP (16/32/64) registers are
 // sorted by a Batcher odd-even merge network of VIMNMX.U16x2 min/max pairs:
 // every compare-exchange orders both pixels at once, every index is a
-// compile-time constant, nothing leaves the register file.  The sorted columns
-// are then parked in shared memory (one conflict-free 4-byte store per frame)
-// where the iterative, data-dependent part of the rejection (ssc_column.cuh)
-// indexes them dynamically.
+// compile-time constant, nothing leaves the register file.
+//
+// Instruction-cache economy decides the rest (tools/micro/ifetch.cu):
+// an SM serves ~32 KB of straight-line code at full rate, and a 64-frame tile
+// with an unrolled gather and normalization is 48 KB.  So 64-frame stacks are
+// STAGED: one cp.async per frame into the thread's shared-memory column, a
+// rolled loop that normalizes the column in place and takes the exact sums,
+// NP static loads into the registers of the network.  Stacks of <= 32 frames
+// keep the fully unrolled form (their code is small).
+//
+// Sigma clipping on full stacks of 32/64 frames (MODE_SIGMA_REG) never leaves
+// the registers for most pixels: a conservative single-precision test on the
+// extremes proves that nothing is rejected (clip_cannot_fire); the others are
+// packed into 48-byte items on a per-warp shared-memory queue and evaluated
+// exactly in FP64, one pixel per lane with full warps, one clipping pass per
+// round.  The other modes park the sorted columns in shared memory, where the
+// iterative, data-dependent rejection code (ssc_column.cuh) indexes them
+// dynamically through a per-block work queue.
 //
 // Normalization (stacking.c:1635-1652) keeps the reference's individually
-// rounded FP64 operations but avoids the slow int<->double conversion units:
-// WORD -> double through the 2^52 mantissa trick, round_to_WORD through an
-// add in round-toward-zero mode onto 1.5*2^52 (floor in the low word) and one
-// VIMNMX.RELU clamp.  Both are exact; frames whose coefficients would leave
-// the trick's domain (|value| >= 2^31) take the conversion-based form instead.
+// rounded FP64 operations but avoids the slow double->int conversion unit:
+// round_to_WORD through an add in round-toward-zero mode onto 1.5*2^52 (floor
+// in the low word) and one VIMNMX.RELU clamp.  Exact; frames whose coefficients
+// would leave the trick's domain (|value| >= 2^31) take the conversion-based
+// form instead.
 #include <cstdlib>
 #include "ssc_column.cuh"
 #include "ssc_kernels.h"
