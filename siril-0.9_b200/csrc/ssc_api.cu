@@ -809,6 +809,7 @@ int ssc_release_workspace(void) {
 	for (auto &kv : g_cache) {
 		cudaSetDevice(kv.first);
 		kv.second.release();
+		ssc::release_kernel_scratch(kv.first);
 	}
 	g_cache.clear();
 	if (g_pinned) cudaFreeHost(g_pinned);

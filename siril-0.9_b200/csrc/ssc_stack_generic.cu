@@ -12,6 +12,7 @@
 // the rare history-dependent pixels back to this one.
 #include "ssc_column.cuh"
 #include "ssc_kernels.h"
+#include "ssc_leftover.cuh"
 
 namespace ssc {
 
@@ -184,6 +185,21 @@ static int fit_tables(FitTables &fit, cudaStream_t stream) {
 	fit.mdx2 = g_fit_store[dev] + 2 * stride;
 	fit.n_max = n_max;
 	return SSC_OK;
+}
+
+// frees the per-device scratch the kernels keep between launches (ssc_release_workspace)
+void release_kernel_scratch(int dev) {
+	if (dev < 0 || dev >= 64) return;
+	if (g_fit_store[dev]) { cudaFree(g_fit_store[dev]); g_fit_store[dev] = nullptr; }
+	LeftoverIdStore &ids = g_leftover_id_store[dev];
+	if (ids.ids) cudaFree(ids.ids);
+	if (ids.count) cudaFree(ids.count);
+	ids = LeftoverIdStore{};
+	LeftoverStore &st = g_leftover_store[dev];
+	if (st.cols) cudaFree(st.cols);
+	if (st.meta) cudaFree(st.meta);
+	if (st.count) cudaFree(st.count);
+	st = LeftoverStore{};
 }
 
 int g_kernel_path = 0;

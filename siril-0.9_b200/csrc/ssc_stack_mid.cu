@@ -11,9 +11,10 @@
 //      over shared memory (the partner of element k of one run is element L-1-k of the other), the last
 //      six stages of every 64-element block run in registers again (192 compare-exchanges);
 //   5. the sorted column goes through the same per-pixel rejection code as the general kernel
-//      (ssc_column.cuh).  The block has twice as many threads as pixel pairs: the second half idles at a
-//      barrier through 1-4 and takes the second pixel of every pair here, so the serial per-pixel loops
-//      (winsorization, linear fit) run one pixel per thread.
+//      (ssc_column.cuh).
+// The block has twice as many threads as pixel pairs: in 1-4 each of a pair's two threads works on one
+// half of the column (only the last merge level is shared), in 5 each takes one pixel of the pair, so
+// the serial per-pixel loops (winsorization, linear fit) run one pixel per thread.
 // Per pixel this is ~9 k instructions against ~50 k for the general kernel's shared-memory bitonic sort.
 #include "ssc_column.cuh"
 #include "ssc_kernels.h"
@@ -38,10 +39,10 @@ __device__ __forceinline__ void bitonic_merge_64(unsigned int (&v)[64]) {
 }
 
 template <int KIND, int MID_THREADS, int NPAD>
-__device__ __forceinline__ void normalize_column(unsigned int *col_t, const double *s_coef, int N,
+__device__ __forceinline__ void normalize_column(unsigned int *col_t, const double *s_coef, int f_begin, int N,
 		unsigned int &Sa, unsigned int &Sb, unsigned long long &Qa, unsigned long long &Qb) {
 #pragma unroll 1
-	for (int f0 = 0; f0 < N; f0 += 4) {
+	for (int f0 = f_begin; f0 < N; f0 += 4) {	// frames [f_begin, N), f_begin a multiple of 4
 		unsigned int w[4];
 		double off[4], mul[4], sc[4];
 #pragma unroll
@@ -78,13 +79,12 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 	__shared__ double s_coef[3 * NPAD];			// offset, mul, scale
 	__shared__ int s_fast_norm;
 	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
-	__shared__ unsigned long long s_S[2 * MID_THREADS], s_Q[2 * MID_THREADS];	// per pixel: [h * MID_THREADS + pair]
+	__shared__ unsigned long long s_S[4 * MID_THREADS], s_Q[4 * MID_THREADS];	// [half of the column][pixel * MID_THREADS + pair]
 	__shared__ unsigned int s_out[MID_THREADS];		// per pair: result index, bit 31 = inactive
 	__shared__ unsigned char s_layer[MID_THREADS];
 
 	const ssc_band &b = p.band;
 	const int W = b.width, W2 = W >> 1, N = b.n_frames, tid = threadIdx.x;
-	const bool sorter = tid < MID_THREADS;
 	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
 	const bool need_sort = is_median || p.rejection != NO_REJEC;
 
@@ -106,13 +106,20 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 	__syncthreads();
 
 	const unsigned int total = (unsigned int) ((unsigned long long) b.layers * b.out_rows * W2);	// < 2^32: mid_path_eligible
-	unsigned int *col_t = col + (tid & (MID_THREADS - 1));
+	// Two threads per pixel pair: thread (pair, half) gathers, normalizes, sorts and merges the half
+	// [half * NPAD/2, (half + 1) * NPAD/2) of the pair's column on its own; the last merge level is
+	// shared (two barriers); then each thread takes one pixel of the pair through the rejection.
+	constexpr int HALF = NPAD / 2;
+	const int pair = tid & (MID_THREADS - 1), half = tid / MID_THREADS;
+	const int h0 = half * HALF;					// my half of the column
+	const int n_end = N < h0 + HALF ? (N > h0 ? N : h0) : h0 + HALF;	// my samples: [h0, n_end)
+	unsigned int *col_t = col + pair;
 	const unsigned int sbase = (unsigned int) __cvta_generic_to_shared(col_t);
 	const unsigned int fstride32 = (unsigned int) (b.frame_stride * sizeof(WORD));
 
 	for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		if (sorter) {
-		unsigned int g = tile * MID_THREADS + tid;
+		{
+		unsigned int g = tile * MID_THREADS + pair;
 		const bool active = g < total;
 		if (!active) g = total - 1;
 		const unsigned int row = g / (unsigned int) W2;
@@ -125,21 +132,21 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 		const unsigned int out_idx = (unsigned int) ((size_t) layer * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W + 2 * x2);
 		const char *src0 = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames) + toff);
 
-		// ---- 1. gather ----
+		// ---- 1. gather (my half of the frames) ----
 #pragma unroll 4
-		for (int f = 0; f < N; f++) {
+		for (int f = h0; f < n_end; f++) {
 			const char *src = src0 + (unsigned long long) ((unsigned int) f) * fstride32;
 			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sbase + f * MID_THREADS * (int) sizeof(unsigned int)), "l"(src) : "memory");
 		}
 		asm volatile("cp.async.commit_group;" ::: "memory");
-		for (int f = N; f < NPAD; f++) col_t[f * MID_THREADS] = 0xFFFFFFFFu;	// sentinels sort behind the samples
+		for (int f = n_end; f < h0 + HALF; f++) col_t[f * MID_THREADS] = 0xFFFFFFFFu;	// sentinels sort behind the samples
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 
-		// ---- 2. normalize in place (stacking.c:1635-1652; median path :750-764), exact sums ----
+		// ---- 2. normalize in place (stacking.c:1635-1652; median path :750-764), exact partial sums ----
 		unsigned int Sa = 0, Sb = 0;
 		unsigned long long Qa = 0, Qb = 0;
 		if (norm && !s_fast_norm) {
-			for (int f = 0; f < N; f++) {
+			for (int f = h0; f < n_end; f++) {
 				const unsigned int w = col_t[f * MID_THREADS];
 				const unsigned int pa = normalize_sample(w & 0xFFFFu, p.normalize, s_coef[f], s_coef[NPAD + f], s_coef[2 * NPAD + f]);
 				const unsigned int pb = normalize_sample(w >> 16, p.normalize, s_coef[f], s_coef[NPAD + f], s_coef[2 * NPAD + f]);
@@ -150,22 +157,56 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 			}
 		} else {
 			switch (norm ? p.normalize : NO_NORM) {
-			case NO_NORM: normalize_column<NO_NORM, MID_THREADS, NPAD>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
-			case ADDITIVE: normalize_column<ADDITIVE, MID_THREADS, NPAD>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
-			case MULTIPLICATIVE: normalize_column<MULTIPLICATIVE, MID_THREADS, NPAD>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
-			case ADDITIVE_SCALING: normalize_column<ADDITIVE_SCALING, MID_THREADS, NPAD>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
-			default: normalize_column<MULTIPLICATIVE_SCALING, MID_THREADS, NPAD>(col_t, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case NO_NORM: normalize_column<NO_NORM, MID_THREADS, NPAD>(col_t, s_coef, h0, n_end, Sa, Sb, Qa, Qb); break;
+			case ADDITIVE: normalize_column<ADDITIVE, MID_THREADS, NPAD>(col_t, s_coef, h0, n_end, Sa, Sb, Qa, Qb); break;
+			case MULTIPLICATIVE: normalize_column<MULTIPLICATIVE, MID_THREADS, NPAD>(col_t, s_coef, h0, n_end, Sa, Sb, Qa, Qb); break;
+			case ADDITIVE_SCALING: normalize_column<ADDITIVE_SCALING, MID_THREADS, NPAD>(col_t, s_coef, h0, n_end, Sa, Sb, Qa, Qb); break;
+			default: normalize_column<MULTIPLICATIVE_SCALING, MID_THREADS, NPAD>(col_t, s_coef, h0, n_end, Sa, Sb, Qa, Qb); break;
 			}
 		}
-		s_S[tid] = Sa; s_S[MID_THREADS + tid] = Sb;
-		s_Q[tid] = Qa; s_Q[MID_THREADS + tid] = Qb;
-		s_out[tid] = out_idx | (active ? 0u : 0x80000000u);
-		s_layer[tid] = (unsigned char) layer;
+		// partial sums of my half, per pixel: [half][pixel * MID_THREADS + pair]
+		s_S[half * 2 * MID_THREADS + pair] = Sa; s_S[half * 2 * MID_THREADS + MID_THREADS + pair] = Sb;
+		s_Q[half * 2 * MID_THREADS + pair] = Qa; s_Q[half * 2 * MID_THREADS + MID_THREADS + pair] = Qb;
+		if (half == 0) {
+			s_out[pair] = out_idx | (active ? 0u : 0x80000000u);
+			s_layer[pair] = (unsigned char) layer;
+		}
+		}
+
+		// the last six stages of a bitonic merge for the 64-element blocks of [first, first + len)
+		auto block_merges = [&](int first, int len) {
+#pragma unroll 1
+			for (int c0 = first; c0 < first + len; c0 += 64) {
+				unsigned int v[64];
+				unsigned int *blk = col_t + c0 * MID_THREADS;
+#pragma unroll
+				for (int k = 0; k < 64; k++) v[k] = blk[k * MID_THREADS];
+				bitonic_merge_64(v);
+#pragma unroll
+				for (int k = 0; k < 64; k++) blk[k * MID_THREADS] = v[k];
+			}
+		};
+		// half-cleaners at distances d_first, d_first / 2, ... 64 over [first, first + len)
+		auto half_cleaners = [&](int first, int len, int d_first, int log_d_first) {
+			int log_d = log_d_first;
+#pragma unroll 1
+			for (int d = d_first; d >= 64; d >>= 1, log_d--) {
+#pragma unroll 2
+				for (int j = 0; j < len / 2; j++) {
+					const int blk = j >> log_d, k = j & (d - 1);
+					unsigned int *lo = col_t + (first + blk * 2 * d + k) * MID_THREADS;
+					unsigned int *hi = lo + d * MID_THREADS;
+					const unsigned int x = *lo, y = *hi;
+					*lo = __vminu2(x, y);
+					*hi = __vmaxu2(x, y);
+				}
+			}
+		};
 
 		if (need_sort) {
-			// ---- 3. runs of 64 through the register network ----
+			// ---- 3. my runs of 64 through the register network ----
 #pragma unroll 1
-			for (int c0 = 0; c0 < N; c0 += 64) {
+			for (int c0 = h0; c0 < n_end; c0 += 64) {
 				unsigned int v[64];
 				unsigned int *blk = col_t + c0 * MID_THREADS;
 #pragma unroll
@@ -174,48 +215,41 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 #pragma unroll
 				for (int k = 0; k < 64; k++) blk[k * MID_THREADS] = v[k];
 			}
-			// ---- 4. bitonic merges of runs of L = 64, 128, ... NPAD / 2 ----
+			// ---- 4a. bitonic merges inside my half: runs of L = 64, 128, ... HALF / 2 ----
 			int log_l = 6;
 #pragma unroll 1
-			for (int L = 64; L < NPAD; L <<= 1, log_l++) {
+			for (int L = 64; L < HALF; L <<= 1, log_l++) {
 				// first stage: element k of the lower run against element L-1-k of the upper run
 #pragma unroll 2
-				for (int j = 0; j < NPAD / 2; j++) {
+				for (int j = 0; j < HALF / 2; j++) {
 					const int blk = j >> log_l, k = j & (L - 1);
-					unsigned int *lo = col_t + (blk * 2 * L + k) * MID_THREADS;
-					unsigned int *hi = col_t + (blk * 2 * L + 2 * L - 1 - k) * MID_THREADS;
+					unsigned int *lo = col_t + (h0 + blk * 2 * L + k) * MID_THREADS;
+					unsigned int *hi = col_t + (h0 + blk * 2 * L + 2 * L - 1 - k) * MID_THREADS;
 					const unsigned int x = *lo, y = *hi;
 					*lo = __vminu2(x, y);
 					*hi = __vmaxu2(x, y);
 				}
-				// half-cleaners at distances L/2 ... 64
-				int log_d = log_l - 1;
-#pragma unroll 1
-				for (int d = L >> 1; d >= 64; d >>= 1, log_d--) {
+				half_cleaners(h0, HALF, L >> 1, log_l - 1);
+				block_merges(h0, HALF);
+			}
+			__syncthreads();
+			// ---- 4b. the last level, L = HALF: its first stage is shared between the two threads ----
 #pragma unroll 2
-					for (int j = 0; j < NPAD / 2; j++) {
-						const int blk = j >> log_d, k = j & (d - 1);
-						unsigned int *lo = col_t + (blk * 2 * d + k) * MID_THREADS;
-						unsigned int *hi = lo + d * MID_THREADS;
-						const unsigned int x = *lo, y = *hi;
-						*lo = __vminu2(x, y);
-						*hi = __vmaxu2(x, y);
-					}
-				}
-				// the last six stages of every 64-element block, in registers
-#pragma unroll 1
-				for (int c0 = 0; c0 < NPAD; c0 += 64) {
-					unsigned int v[64];
-					unsigned int *blk = col_t + c0 * MID_THREADS;
-#pragma unroll
-					for (int k = 0; k < 64; k++) v[k] = blk[k * MID_THREADS];
-					bitonic_merge_64(v);
-#pragma unroll
-					for (int k = 0; k < 64; k++) blk[k * MID_THREADS] = v[k];
-				}
+			for (int j = half * (HALF / 2); j < (half + 1) * (HALF / 2); j++) {
+				unsigned int *lo = col_t + j * MID_THREADS;
+				unsigned int *hi = col_t + (NPAD - 1 - j) * MID_THREADS;
+				const unsigned int x = *lo, y = *hi;
+				*lo = __vminu2(x, y);
+				*hi = __vmaxu2(x, y);
+			}
+			__syncthreads();
+			{
+				int log_h = 6;
+				for (int t = 64; t < HALF; t <<= 1) log_h++;	// log2(HALF)
+				half_cleaners(h0, HALF, HALF >> 1, log_h - 1);	// my half is bitonic now
+				block_merges(h0, HALF);
 			}
 		}
-		}	// sorter
 		__syncthreads();
 
 		// ---- 5. per-pixel tail on the sorted column: thread t takes pixel t / MID_THREADS of pair t % MID_THREADS ----
@@ -230,7 +264,8 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 				res = (c.get((N - 1) >> 1) + c.get(N >> 1)) >> 1;
 			} else {
 				RejectState st{0, 0, 0, 0};
-				res = reject_sorted_and_mean<false>(c, N, p.rejection, p.sig_low, p.sig_high, s_S[tid], s_Q[tid], st, nullptr, &p.fit);
+				const unsigned long long S = s_S[tid] + s_S[2 * MID_THREADS + tid], Q = s_Q[tid] + s_Q[2 * MID_THREADS + tid];
+				res = reject_sorted_and_mean<false>(c, N, p.rejection, p.sig_low, p.sig_high, S, Q, st, nullptr, &p.fit);
 				if (active) {
 					if (st.rej_lo) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) st.rej_lo);
 					if (st.rej_hi) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) st.rej_hi);
