@@ -40,6 +40,7 @@ int launch_stack_fast(const StackParams &p, int is_median, cudaStream_t stream);
 // ssc_stack_mid.cu: 65..256 frames, register network on runs of 64 + shared-memory merges
 bool mid_path_eligible(const StackParams &p, int is_median);
 int launch_stack_mid(const StackParams &p, int is_median, cudaStream_t stream);
+void release_mid_scratch(int dev);
 // ssc_stack_pipe.cu
 bool pipe_path_eligible(const StackParams &p, int is_median);
 int launch_stack_pipe(const StackParams &p, cudaStream_t stream);

@@ -191,6 +191,7 @@ static int fit_tables(FitTables &fit, cudaStream_t stream) {
 void release_kernel_scratch(int dev) {
 	if (dev < 0 || dev >= 64) return;
 	if (g_fit_store[dev]) { cudaFree(g_fit_store[dev]); g_fit_store[dev] = nullptr; }
+	release_mid_scratch(dev);
 	LeftoverIdStore &ids = g_leftover_id_store[dev];
 	if (ids.ids) cudaFree(ids.ids);
 	if (ids.count) cudaFree(ids.count);

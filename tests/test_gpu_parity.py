@@ -347,6 +347,20 @@ def test_mid_kernel_equals_general_kernel(gpu, port, rej, n, norm):
         assert a.guard_fired == same["guard_fired"]
 
 
+def test_mid_kernel_linear_fit_in_row_slices(gpu, port, monkeypatch):
+    """Linear fit on 65..1024 frames spills the sorted columns to global memory and walks the band in row
+    slices (ssc_stack_mid.cu); a tiny spill area forces many slices, RGB and an odd slice remainder."""
+    fr = synth.make_frames(72, 3, 11, 40, seed=12, outlier_p=8e-3, zero_p=2e-3, stars=2)
+    monkeypatch.setenv("SSC_SPILL_BYTES", str(3 * 40 * 3 * (72 * 2 + 21)))          # three rows per slice
+    res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), 5, (5.0, 2.5), 3)
+    monkeypatch.delenv("SSC_SPILL_BYTES")
+    one = gpu.stack_mean_with_rejection(gpu.Sequence(fr), 5, (5.0, 2.5), 3)            # one slice
+    same = port.stack_mean(fr, 5, (5.0, 2.5), 3, coeff=res.coeff, sd_mode=port.SD_EXACT)
+    for r in (res, one):
+        assert np.array_equal(r.data, same["out"]) and np.array_equal(r.irej, same["irej"])
+        assert r.guard_fired == same["guard_fired"]
+
+
 def test_mid_kernel_rgb_ser_and_fallbacks(gpu, port):
     """RGB + SER row order on the mid kernel; an odd width and registration shifts must fall back to the
     general kernel and still agree with the oracle."""
