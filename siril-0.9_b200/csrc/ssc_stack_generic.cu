@@ -214,7 +214,8 @@ int launch_stack(const StackParams &p_in, int is_median, cudaStream_t stream) {
 	}
 	if (g_kernel_path == 2 && pipe_path_eligible(p, is_median))
 		return launch_stack_pipe(p, stream);	// experimental (slower than the register kernel so far)
-	if (g_kernel_path != 1 && fast_path_eligible(p, is_median))
+	const bool spilled_fit = !is_median && p.rejection == LINEARFIT && mid_path_eligible(p, is_median);
+	if (g_kernel_path != 1 && !spilled_fit && fast_path_eligible(p, is_median))
 		return launch_stack_fast(p, is_median, stream);
 	if (g_kernel_path != 1 && mid_path_eligible(p, is_median))
 		return launch_stack_mid(p, is_median, stream);

@@ -353,7 +353,10 @@ void release_mid_scratch(int dev) {
 // Same conditions as the 64-frame register kernel (ssc_stack_fast.cu), for 65..1024 frames.
 bool mid_path_eligible(const StackParams &p, int is_median) {
 	const ssc_band &b = p.band;
-	if (b.n_frames <= 64 || b.n_frames > 1024) return false;
+	if (b.n_frames > 1024) return false;
+	// (up to 64 frames the register kernel is the better sorter -- except for the linear fit, whose
+	// rejection dominates and runs best from spilled columns: launch_stack sends it here)
+	if (b.n_frames <= 64 && (is_median || p.rejection != LINEARFIT || b.n_frames < 8)) return false;
 	if (!is_median && (b.shiftx || b.shifty)) return false;
 	if ((b.width & 1) || (b.frame_stride & 1) || (b.layer_stride & 1)) return false;
 	if (((uintptr_t) b.frames & 3) || ((uintptr_t) p.out & 3) || (p.out_layer_stride & 1)) return false;
