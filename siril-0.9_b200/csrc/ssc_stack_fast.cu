@@ -137,10 +137,13 @@ constexpr int FAST_QUEUE_WORDS = 12, FAST_QUEUE_CAP = 96;	// per warp: < 32 wait
 //       sensitive, dead alternatives are not carried along)
 constexpr int FAST_THREADS = 128;	// 4 blocks per SM (measured: 256/512-thread blocks, tile barriers and warp ping-pong are no faster)
 
-template <int NP, bool FULL, int MODE>
+// ROWTILE (MODE_SIGMA_REG only): a warp's 32 pixel pairs are consecutive in ONE row and rows are
+// 16-byte aligned, so the gather is sixteen 16-byte copies per thread and tile (each lane fetches four
+// pairs of a frame for its neighbours) instead of 64 4-byte copies with their address arithmetic
+template <int NP, bool FULL, int MODE, bool ROWTILE = false>
 __global__ void __launch_bounds__(FAST_THREADS, 4)
 k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
-	extern __shared__ unsigned int cols[];		// [NP][FAST_THREADS] packed columns
+	extern __shared__ __align__(16) unsigned int cols[];	// [NP][FAST_THREADS] packed columns
 	__shared__ double s_coef[3 * 64];
 	__shared__ double s_unbias[65], s_inv_n[65], s_inv_n2[65];	// small-n tables (ssc_device.cuh)
 	__shared__ int s_fast_norm;
@@ -196,30 +199,75 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	// MODE_SIGMA_REG: request a tile's samples (see the gather below); pf_* describe the requested tile
 	int pf_layer = 0;
 	unsigned int pf_out_idx = 0;
+	bool pf_active = false;
 	const bool punt_all = MODE == MODE_SIGMA_REG && norm && !s_fast_norm;
-	auto issue_tile = [&](unsigned long long t) {
+	const int warp = tid >> 5;
+	const unsigned int xblocks = ((unsigned int) W2 + 31u) >> 5;	// ROWTILE: warp tiles per row
+	// the thread's staging column: element f at stage_t[f * stage_stride]
+	unsigned int *const stage_t = ROWTILE ? cols + warp * NP * 32 + lane : cols + tid;
+	constexpr int stage_stride = ROWTILE ? 32 : FAST_THREADS;
+	// where tile t puts this thread: layer, result row (relative), pixel pair in the row
+	auto locate = [&](unsigned long long t, int &lay, int &rr, int &x2, int &x_warp) -> bool {
 		// (fast_path_eligible guarantees 32-bit pixel counts and frame strides: no 64-bit division)
-		unsigned long long gg = t * FAST_THREADS + tid;
-		if (gg >= total) gg = total - 1;
-		const unsigned int g32 = (unsigned int) gg, row = g32 / (unsigned int) W2;
-		const int x2 = (int) (g32 - row * (unsigned int) W2);
-		const int lay = (int) (row / (unsigned int) b.out_rows);
-		const int rr = (int) (row - (unsigned int) lay * (unsigned int) b.out_rows);
+		if constexpr (ROWTILE) {
+			const unsigned int wt = (unsigned int) t * (FAST_THREADS / 32) + warp;
+			const unsigned int n_wt = (unsigned int) b.layers * (unsigned int) b.out_rows * xblocks;
+			const unsigned int wc = wt < n_wt ? wt : n_wt - 1;
+			const unsigned int row = wc / xblocks, xb = wc - row * xblocks;
+			lay = (int) (row / (unsigned int) b.out_rows);
+			rr = (int) (row - (unsigned int) lay * (unsigned int) b.out_rows);
+			x_warp = (int) (xb * 32);		// the warp's first pair
+			x2 = x_warp + lane;
+			const bool ok = wt < n_wt && x2 < W2;
+			if (x2 >= W2) x2 = W2 - 1;
+			return ok;
+		} else {
+			unsigned long long gg = t * FAST_THREADS + tid;
+			const bool ok = gg < total;
+			if (!ok) gg = total - 1;
+			const unsigned int g32 = (unsigned int) gg, row = g32 / (unsigned int) W2;
+			x2 = (int) (g32 - row * (unsigned int) W2);
+			lay = (int) (row / (unsigned int) b.out_rows);
+			rr = (int) (row - (unsigned int) lay * (unsigned int) b.out_rows);
+			x_warp = 0;
+			return ok;
+		}
+	};
+	auto issue_tile = [&](unsigned long long t) {
+		int lay, rr, x2, x_warp;
+		pf_active = locate(t, lay, rr, x2, x_warp);
 		const int R = b.out_row0 + rr;				// result storage row (stacking.c:731,1600)
 		const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - R : R;
-		const unsigned int toff = (unsigned int) ((((size_t) lay * b.layer_stride + (size_t) (srow - b.buf_row0) * W) >> 1) + x2);
 		pf_layer = lay;
 		pf_out_idx = (unsigned int) ((size_t) lay * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W + 2 * x2);
-		const char *src0 = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames) + toff);
 		const unsigned int fstride32 = (unsigned int) (b.frame_stride * sizeof(WORD));
-		const unsigned int sbase = (unsigned int) __cvta_generic_to_shared(cols + tid);
+		const size_t row_word = ((size_t) lay * b.layer_stride + (size_t) (srow - b.buf_row0) * W) >> 1;	// first pair of the row
+		if constexpr (ROWTILE) {
+			// lane = 8 * s + c fetches pairs [4c, 4c + 4) of the warp's 32 for frames s, s + 4, s + 8, ...
+			const int c = lane & 7, sub = lane >> 3;
+			const int xw = x_warp + 4 * c;			// first pair of my chunk
+			const bool chunk_ok = xw < W2;			// W2 % 4 == 0: a chunk is inside the row or outside
+			const char *src0 = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames) + row_word + xw)
+					+ (unsigned long long) ((unsigned int) sub) * fstride32;
+			const unsigned int sbase = (unsigned int) __cvta_generic_to_shared(cols + warp * NP * 32 + sub * 32 + 4 * c);
+			if (chunk_ok) {
 #pragma unroll 4
-		for (int k = 0; k < NP; k++) {
-			if (FULL || k < N) {
-				const char *src = src0 + (unsigned long long) ((unsigned int) k) * fstride32;	// one IMAD.WIDE
-				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sbase + k * FAST_THREADS * (int) sizeof(unsigned int)), "l"(src) : "memory");
-			} else {
-				cols[k * FAST_THREADS + tid] = 0xFFFFFFFFu;	// sentinels sort behind the N samples
+				for (int i = 0; i < NP / 4; i++) {
+					const char *src = src0 + (unsigned long long) ((unsigned int) (4 * i)) * fstride32;
+					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + i * 4 * 32 * (int) sizeof(unsigned int)), "l"(src) : "memory");
+				}
+			}
+		} else {
+			const char *src0 = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames) + row_word + x2);
+			const unsigned int sbase = (unsigned int) __cvta_generic_to_shared(cols + tid);
+#pragma unroll 4
+			for (int k = 0; k < NP; k++) {
+				if (FULL || k < N) {
+					const char *src = src0 + (unsigned long long) ((unsigned int) k) * fstride32;	// one IMAD.WIDE
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sbase + k * FAST_THREADS * (int) sizeof(unsigned int)), "l"(src) : "memory");
+				} else {
+					cols[k * FAST_THREADS + tid] = 0xFFFFFFFFu;	// sentinels sort behind the N samples
+				}
 			}
 		}
 		asm volatile("cp.async.commit_group;" ::: "memory");
@@ -233,11 +281,14 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	if (MODE != MODE_SIGMA_REG && !more) break;
 	if (more) {
 	unsigned long long g = tile * FAST_THREADS + tid;
-	const bool active = g < total;
+	bool active = g < total;
 	if constexpr (MODE == MODE_SIGMA_REG) {
 		if (punt_all) {	// coefficients outside the fast normalization's domain (block-uniform):
-			leftover_push(list, active, (unsigned int) (2 * g), lane);		// every pixel goes to the
-			leftover_push(list, active, (unsigned int) (2 * g + 1), lane);	// general kernel
+			int lay, rr, x2, x_warp;
+			const bool ok = locate(tile, lay, rr, x2, x_warp);
+			const unsigned int pix = (unsigned int) (((size_t) lay * b.out_rows + rr) * W + 2 * x2);
+			leftover_push(list, ok, pix, lane);		// every pixel goes to the general kernel
+			leftover_push(list, ok, pix + 1, lane);
 			continue;
 		}
 	}
@@ -258,22 +309,24 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 		if constexpr (!PREFETCH) issue_tile(tile);
 		layer = pf_layer;
 		out_idx = pf_out_idx;
-		unsigned int *stage_t = cols + tid;
+		active = pf_active;
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		if constexpr (ROWTILE) __syncwarp();	// the lanes fetched each other's samples
 		if (norm && !s_fast_norm) {
-			normalize_staged_slow(stage_t, FAST_THREADS, s_coef, N, p.normalize, Sa, Sb, Qa, Qb);
+			normalize_staged_slow(stage_t, stage_stride, s_coef, N, p.normalize, Sa, Sb, Qa, Qb);
 		} else {
 			switch (norm ? p.normalize : NO_NORM) {
-			case NO_NORM: normalize_staged<NP, NO_NORM, FULL>(stage_t, FAST_THREADS, s_coef, N, Sa, Sb, Qa, Qb); break;
-			case ADDITIVE: normalize_staged<NP, ADDITIVE, FULL>(stage_t, FAST_THREADS, s_coef, N, Sa, Sb, Qa, Qb); break;
-			case MULTIPLICATIVE: normalize_staged<NP, MULTIPLICATIVE, FULL>(stage_t, FAST_THREADS, s_coef, N, Sa, Sb, Qa, Qb); break;
-			case ADDITIVE_SCALING: normalize_staged<NP, ADDITIVE_SCALING, FULL>(stage_t, FAST_THREADS, s_coef, N, Sa, Sb, Qa, Qb); break;
-			default: normalize_staged<NP, MULTIPLICATIVE_SCALING, FULL>(stage_t, FAST_THREADS, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case NO_NORM: normalize_staged<NP, NO_NORM, FULL>(stage_t, stage_stride, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case ADDITIVE: normalize_staged<NP, ADDITIVE, FULL>(stage_t, stage_stride, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case MULTIPLICATIVE: normalize_staged<NP, MULTIPLICATIVE, FULL>(stage_t, stage_stride, s_coef, N, Sa, Sb, Qa, Qb); break;
+			case ADDITIVE_SCALING: normalize_staged<NP, ADDITIVE_SCALING, FULL>(stage_t, stage_stride, s_coef, N, Sa, Sb, Qa, Qb); break;
+			default: normalize_staged<NP, MULTIPLICATIVE_SCALING, FULL>(stage_t, stage_stride, s_coef, N, Sa, Sb, Qa, Qb); break;
 			}
 		}
 #pragma unroll
-		for (int k = 0; k < NP; k++) v[k] = stage_t[k * FAST_THREADS];
+		for (int k = 0; k < NP; k++) v[k] = stage_t[k * stage_stride];
 		have_q = true;
+		if constexpr (ROWTILE) __syncwarp();	// everybody has its column: the buffer may be refilled
 		if (PREFETCH && tile + gridDim.x < n_tiles) issue_tile(tile + gridDim.x);
 	} else {
 	if (!active) g = total - 1;
@@ -612,7 +665,7 @@ bool fast_path_eligible(const StackParams &p, int is_median) {
 	return true;
 }
 
-template <int NP, bool FULL, int MODE>
+template <int NP, bool FULL, int MODE, bool ROWTILE = false>
 static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 	const ssc_band &b = p.band;
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * (b.width >> 1);
@@ -621,16 +674,19 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 			? (size_t) NP * FAST_THREADS * sizeof(unsigned int)
 				+ (size_t) (FAST_THREADS / 32) * FAST_QUEUE_WORDS * FAST_QUEUE_CAP * sizeof(unsigned int)
 			: (size_t) NP * FAST_THREADS * sizeof(unsigned int);
-	if (cudaFuncSetAttribute(k_stack_fast<NP, FULL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
+	if (cudaFuncSetAttribute(k_stack_fast<NP, FULL, MODE, ROWTILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
-	const unsigned long long tiles = (total + FAST_THREADS - 1) / FAST_THREADS;
+	// ROWTILE: tiles of four warp tiles, each 32 consecutive pairs of one row
+	const unsigned long long tiles = ROWTILE
+			? ((unsigned long long) b.layers * b.out_rows * (((b.width >> 1) + 31) / 32) + FAST_THREADS / 32 - 1) / (FAST_THREADS / 32)
+			: (total + FAST_THREADS - 1) / FAST_THREADS;
 	if (tiles > 0x7FFFFFFFull) return SSC_ERR_ARG;
 	unsigned long long blocks = tiles;
 	{	// a bounded grid of looping blocks: 4 per resident slot measured best (SSC_FAST_WAVES overrides)
 		int dev = 0, sms = 148, per_sm = 1;
 		cudaGetDevice(&dev);
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stack_fast<NP, FULL, MODE>, FAST_THREADS, smem) != cudaSuccess || per_sm < 1)
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stack_fast<NP, FULL, MODE, ROWTILE>, FAST_THREADS, smem) != cudaSuccess || per_sm < 1)
 			per_sm = 1;
 		static int waves = 0;
 		if (!waves) { const char *e = getenv("SSC_FAST_WAVES"); waves = e ? atoi(e) : 4; if (waves < 1) waves = 1; }
@@ -642,7 +698,7 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 		int rc = leftover_ids(total * 2, list, stream);
 		if (rc) return rc;
 	}
-	k_stack_fast<NP, FULL, MODE><<<(unsigned int) blocks, FAST_THREADS, smem, stream>>>(p, list, (unsigned int) tiles);
+	k_stack_fast<NP, FULL, MODE, ROWTILE><<<(unsigned int) blocks, FAST_THREADS, smem, stream>>>(p, list, (unsigned int) tiles);
 	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
 	if constexpr (MODE == MODE_SIGMA_REG)	// the pixels that left the candidate window: general kernel, list mode
 		return launch_stack_generic(p, list.ids, list.count, list.capacity, 0, stream);
@@ -658,8 +714,13 @@ static int launch_fast_np(const StackParams &p, int is_median, cudaStream_t stre
 		return full ? launch_fast_cfg<NP, true, MODE_NOREJ>(p, stream) : launch_fast_cfg<NP, false, MODE_NOREJ>(p, stream);
 	if constexpr (NP >= 32) {
 		// (non-negative parameters: a sample above the median is then never "low", one below never "high")
-		if (full && p.rejection == SIGMA && p.sig_low >= 0.0 && p.sig_high >= 0.0)
-			return launch_fast_cfg<NP, true, MODE_SIGMA_REG>(p, stream);
+		if (full && p.rejection == SIGMA && p.sig_low >= 0.0 && p.sig_high >= 0.0) {
+			const ssc_band &b = p.band;	// rows on 16-byte boundaries: the 16-byte gather (ROWTILE)
+			const bool rows16 = b.width % 8 == 0 && b.frame_stride % 8 == 0 && b.layer_stride % 8 == 0
+					&& ((uintptr_t) b.frames & 15) == 0;
+			return rows16 ? launch_fast_cfg<NP, true, MODE_SIGMA_REG, true>(p, stream)
+					: launch_fast_cfg<NP, true, MODE_SIGMA_REG, false>(p, stream);
+		}
 	}
 	return full ? launch_fast_cfg<NP, true, MODE_QUEUE>(p, stream) : launch_fast_cfg<NP, false, MODE_QUEUE>(p, stream);
 }

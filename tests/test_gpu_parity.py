@@ -406,6 +406,18 @@ def test_sigma_register_kernel_hand_backs(gpu, port, n):
         assert np.array_equal(res.data, same["out"]) and np.array_equal(res.irej, same["irej"]), norm
 
 
+@pytest.mark.parametrize("w", [36, 40, 72, 200])
+def test_sigma_register_kernel_gather_variants(gpu, port, w):
+    """The 32/64-frame sigma kernel gathers with 16-byte copies when rows sit on 16-byte boundaries
+    (width % 8 == 0; w = 40, 72, 200: partial and several warp tiles per row) and with 4-byte copies
+    otherwise (w = 36); RGB, both row orders."""
+    fr = synth.make_frames(32, 3, 7, w, seed=w, outlier_p=8e-3, zero_p=2e-3, stars=2)
+    for ro in (0, 1):
+        res = gpu.stack_mean_with_rejection(gpu.Sequence(fr, row_order=ro), 2, (4.0, 3.0), 2)
+        same = port.stack_mean(fr, 2, (4.0, 3.0), 2, coeff=res.coeff, row_order=ro, sd_mode=port.SD_EXACT)
+        assert np.array_equal(res.data, same["out"]) and np.array_equal(res.irej, same["irej"]), (w, ro)
+
+
 def test_fast_normalization_domain_fallback(gpu, port):
     """Coefficients outside the domain of the 2^52 conversion tricks (a nearly black frame against a
     bright reference: mul ~ 5e4, products beyond 2^31) take the conversion-based normalization."""
