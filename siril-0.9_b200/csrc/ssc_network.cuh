@@ -48,7 +48,7 @@ __device__ __forceinline__ unsigned int normalize_pair_fast(unsigned int w, doub
 	const unsigned int ra = round_to_word_fast(da), rb = round_to_word_fast(db);
 	Qa += (unsigned long long) ra * ra;	// IMAD.WIDE on the values while they are still unpacked
 	Qb += (unsigned long long) rb * rb;
-	return __byte_perm(ra, rb, 0x5410);	// one PRMT: ra | rb << 16 (both below 2^16)
+	return rb * 65536u + ra;	// one IMAD on the FMA pipe (= ra | rb << 16, both below 2^16): the ALU pipe is the busy one
 }
 
 }  // namespace ssc
