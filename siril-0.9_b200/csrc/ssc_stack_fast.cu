@@ -652,6 +652,74 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 		atomicAdd(&p.counters[tid], blk_counters[tid]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The pixels MODE_SIGMA_REG hands back (more rejections than its candidate window holds, or
+// coefficients outside the fast normalization's domain): one thread per listed pixel reloads the
+// column, normalizes it with the conversion-based form, sorts it with the same register network
+// (one sample per register) and runs the complete sigma clipping of ssc_column.cuh on a
+// shared-memory copy.  (The general kernel's list mode did this with a serial shared-memory bitonic
+// sort: ~100 us of latency per launch whatever the list length.)
+// ---------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(128)
+k_sigma_handback(StackParams p, LeftoverList list) {
+	__shared__ WORD col[NP * 128];
+	__shared__ double s_unbias[65], s_inv_n[65], s_inv_n2[65];
+	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
+	const int tid = threadIdx.x;
+	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
+	if (tid >= 1 && tid <= 64) {
+		s_unbias[tid] = tid > 1 ? ddiv((double) tid, (double) (tid - 1)) : 0.0;
+		s_inv_n[tid] = ddiv(1.0, (double) tid);
+		s_inv_n2[tid] = ddiv(1.0, (double) (tid * tid));
+	}
+	const SmallN tables{s_unbias, s_inv_n, s_inv_n2};
+	__syncthreads();
+	const ssc_band &b = p.band;
+	const int W = b.width;
+	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
+	unsigned int n_items = *list.count;
+	if (n_items > list.capacity) n_items = list.capacity;
+	for (unsigned int base = blockIdx.x * 128; base < n_items; base += gridDim.x * 128) {
+		const unsigned int i = base + tid;
+		if (i < n_items) {
+			const unsigned int pix = list.ids[i];
+			const unsigned int row = pix / (unsigned int) W;
+			const int x = (int) (pix - row * (unsigned int) W);
+			const int layer = (int) (row / (unsigned int) b.out_rows);
+			const int rr = (int) (row - (unsigned int) layer * (unsigned int) b.out_rows);
+			const int R = b.out_row0 + rr;
+			const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - R : R;
+			const WORD *src = b.frames + (size_t) layer * b.layer_stride + (size_t) (srow - b.buf_row0) * W + x;
+			unsigned int v[NP];
+#pragma unroll
+			for (int f = 0; f < NP; f++) v[f] = __ldg(src + (size_t) f * b.frame_stride);
+			unsigned long long S = 0, Q = 0;
+			if (norm) {
+#pragma unroll
+				for (int f = 0; f < NP; f++)
+					v[f] = normalize_sample(v[f], p.normalize, p.coeff[f], p.coeff[NP + f], p.coeff[2 * NP + f]);
+			}
+#pragma unroll
+			for (int f = 0; f < NP; f++) { S += v[f]; Q += sq(v[f]); }
+			sort_network<NP>(v);		// packed min/max on values below 2^16: the upper halves stay 0
+			Column c{col + tid, 128};
+#pragma unroll
+			for (int f = 0; f < NP; f++) c.set(f, v[f]);
+			RejectState ist{0, 0, 0, 0};
+			const unsigned int r = reject_sorted_and_mean<true>(c, NP, SIGMA, p.sig_low, p.sig_high, S, Q, ist, &tables);
+			p.out[(size_t) layer * p.out_layer_stride + (size_t) (R - p.out_buf_row0) * W + x] = (WORD) r;
+			if (ist.rej_lo) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) ist.rej_lo);
+			if (ist.rej_hi) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) ist.rej_hi);
+			if (ist.guard) atomicAdd(&blk_counters[6], 1ull);
+			if (ist.cap) atomicAdd(&blk_counters[7], 1ull);
+		}
+	}
+	__syncthreads();
+	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
+		atomicAdd(&p.counters[tid], blk_counters[tid]);
+}
+
 // The register-network kernel applies when two adjacent pixels can be fetched as one
 // aligned 32-bit word from every frame and nothing shifts the frames against each other.
 bool fast_path_eligible(const StackParams &p, int is_median) {
@@ -700,8 +768,13 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 	}
 	k_stack_fast<NP, FULL, MODE, ROWTILE><<<(unsigned int) blocks, FAST_THREADS, smem, stream>>>(p, list, (unsigned int) tiles);
 	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
-	if constexpr (MODE == MODE_SIGMA_REG)	// the pixels that left the candidate window: general kernel, list mode
-		return launch_stack_generic(p, list.ids, list.count, list.capacity, 0, stream);
+	if constexpr (MODE == MODE_SIGMA_REG) {	// the pixels that left the candidate window
+		int dev = 0, sms = 148;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		k_sigma_handback<NP><<<sms * 8, 128, 0, stream>>>(p, list);
+		if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
+	}
 	return SSC_OK;
 }
 
