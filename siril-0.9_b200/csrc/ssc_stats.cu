@@ -191,10 +191,23 @@ int launch_histogram(const ssc_band &b, uint32_t *hist, cudaStream_t stream) {
 	if (cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) HIST_SMEM) != cudaSuccess)
 		return SSC_ERR_CUDA;
 	const size_t band_px = (size_t) b.out_rows * b.width;
-	// one CTA per SM is resident (128 KB of shared memory): spread every frame over
-	// enough CTAs to fill the machine about twice, but keep at least ~32K samples per CTA
-	int per_frame = (2 * sms + b.n_frames - 1) / b.n_frames;
+	// One CTA per SM is resident (136 KB of shared memory) and all CTAs do the same amount of work, so
+	// the launch runs in waves of `sms` CTAs: spread every frame over enough CTAs to fill the machine
+	// at least twice and pick the count whose LAST wave is nearly full (64 frames x 5 parts = 320 CTAs
+	// on 148 SMs ran 3 waves for the work of 2.16), but keep at least ~32K samples per CTA.
 	const size_t max_parts = band_px / 32768 + 1;
+	int per_frame = (2 * sms + b.n_frames - 1) / b.n_frames;
+	{
+		double best = 0.0;
+		int best_p = per_frame;
+		for (int pf = per_frame; pf < per_frame + 32; pf++) {
+			const double waves = (double) b.n_frames * pf / sms;
+			const double eff = waves / (double) (long long) (waves + 0.999999);
+			if (eff > best + 1e-9) { best = eff; best_p = pf; }
+			if (eff >= 0.97) break;
+		}
+		per_frame = best_p;
+	}
 	if ((size_t) per_frame > max_parts) per_frame = (int) max_parts;
 	if (per_frame < 1) per_frame = 1;
 	k_histogram<<<b.n_frames * per_frame, HIST_THREADS, HIST_SMEM, stream>>>(b, hist, per_frame);
