@@ -478,6 +478,21 @@ int run_job(const Job &job) {
 		}
 	}
 
+	// The result (malloc()ed: it becomes gfit.data, stacking.c:776-785) is allocated now and its pages
+	// are touched on a helper thread while the frames upload: first-touch faults on 100+ MB would
+	// otherwise sit between the download and the caller.
+	WORD *result = job.want_coeff_only ? nullptr : (WORD *) malloc(plane * C * sizeof(WORD));
+	struct ResultGuard { WORD *&p; ~ResultGuard() { free(p); } } rguard{result};
+	struct Prefault {
+		std::thread th;
+		void join() { if (th.joinable()) th.join(); }
+		~Prefault() { join(); }
+	} prefault;
+	if (result) {
+		WORD *r = result;
+		const size_t bytes = plane * C * sizeof(WORD);
+		prefault.th = std::thread([r, bytes] { memset(r, 0, bytes); });
+	}
 	mark("planned, workspace ready");
 	double t_h2d = 0, t_dev = 0, t_d2h = 0;
 	auto t_phase = clk::now();
@@ -566,9 +581,7 @@ int run_job(const Job &job) {
 	if (!keep_running()) return fail(SSC_ERR_GENERIC, "cancelled");
 
 	// --- the stack itself ---
-	WORD *result = (WORD *) malloc(plane * C * sizeof(WORD));
 	if (!result) return fail(SSC_ERR_GENERIC, "result allocation failed");
-	struct ResultGuard { WORD *&p; ~ResultGuard() { free(p); } } rguard{result};
 
 	mark("normalization done");
 	log_msg("Starting stacking...\n");
@@ -635,6 +648,7 @@ int run_job(const Job &job) {
 						g_pinned_cap = plane * C * sizeof(WORD);
 				}
 				WORD *landing = g_pinned ? (WORD *) g_pinned : result;
+				prefault.join();	// (long done: the upload took far longer than touching the pages)
 				for (int g = 0; g < G; g++) {
 					Dev &d = devs[g];
 					if (k >= d.pieces.size()) continue;
