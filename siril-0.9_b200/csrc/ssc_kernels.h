@@ -41,13 +41,10 @@ int launch_stack_fast(const StackParams &p, int is_median, cudaStream_t stream);
 bool mid_path_eligible(const StackParams &p, int is_median);
 int launch_stack_mid(const StackParams &p, int is_median, cudaStream_t stream);
 void release_mid_scratch(int dev);
-// ssc_stack_pipe.cu
-bool pipe_path_eligible(const StackParams &p, int is_median);
-int launch_stack_pipe(const StackParams &p, cudaStream_t stream);
 // picks the register-network kernel when the shape allows it, the general kernel otherwise
 int launch_stack(const StackParams &p, int is_median, cudaStream_t stream);
 void release_kernel_scratch(int dev);	// per-device lists and tables the kernels keep between launches
-extern int g_kernel_path;	// 0 automatic, 1 general kernel only, 2 warp-specialised pipeline where eligible (ssc_set_kernel_path)
+extern int g_kernel_path;	// 0 automatic, 1 general kernel only (ssc_set_kernel_path)
 
 // ssc_sum.cu
 int launch_extreme(const ssc_band &b, bool take_max, WORD *out, unsigned int *extreme, cudaStream_t stream);

@@ -761,7 +761,7 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 		const unsigned long long cap = (unsigned long long) sms * per_sm * waves;
 		if (blocks > cap) blocks = cap;
 	}
-	LeftoverList list{nullptr, 0, nullptr, nullptr, nullptr};
+	LeftoverList list{nullptr, 0, nullptr};
 	if (MODE == MODE_SIGMA_REG) {
 		int rc = leftover_ids(total * 2, list, stream);
 		if (rc) return rc;

@@ -196,11 +196,6 @@ void release_kernel_scratch(int dev) {
 	if (ids.ids) cudaFree(ids.ids);
 	if (ids.count) cudaFree(ids.count);
 	ids = LeftoverIdStore{};
-	LeftoverStore &st = g_leftover_store[dev];
-	if (st.cols) cudaFree(st.cols);
-	if (st.meta) cudaFree(st.meta);
-	if (st.count) cudaFree(st.count);
-	st = LeftoverStore{};
 }
 
 int g_kernel_path = 0;
@@ -212,8 +207,6 @@ int launch_stack(const StackParams &p_in, int is_median, cudaStream_t stream) {
 		int rc = fit_tables(p.fit, stream);
 		if (rc) return rc;
 	}
-	if (g_kernel_path == 2 && pipe_path_eligible(p, is_median))
-		return launch_stack_pipe(p, stream);	// experimental (slower than the register kernel so far)
 	const bool spilled_fit = !is_median && p.rejection == LINEARFIT && mid_path_eligible(p, is_median);
 	if (g_kernel_path != 1 && !spilled_fit && fast_path_eligible(p, is_median))
 		return launch_stack_fast(p, is_median, stream);
