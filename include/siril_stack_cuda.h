@@ -223,7 +223,8 @@ typedef struct ssc_band {
 #define SSC_COUNTERS 8
 
 /* K2: stack_median hot loop (stacking.c:746-769).  coeff = device double[3][n_frames]
- * (offset, mul, scale) or NULL for identity.  out: device WORD [layers][out_pitch_rows][width]
+ * (offset, mul, scale) or NULL for identity, as compute_normalization / ssc_dev_norm_coeffs
+ * produce them: scale is 1.0 in the ADDITIVE and MULTIPLICATIVE modes (stacking.c:130-134).  out: device WORD [layers][out_pitch_rows][width]
  * addressed by result storage row - out_buf_row0. */
 int ssc_dev_stack_median(const ssc_band *band, int normalize, const double *coeff,
 		WORD *out, size_t out_layer_stride, int out_buf_row0, void *stream);

@@ -21,7 +21,10 @@
 
 /* src/core/utils.c:68-74 */
 uint16_t so_round_to_word(double x) {
-	if (x <= 0.0)
+	/* NaN (inf - inf with the coefficients of a frame whose IKSS scale is 0): the reference's
+	 * (WORD)(x + 0.5) is undefined in C; its x86-64 build converts through cvttsd2si, whose
+	 * "integer indefinite" 0x80000000 truncates to 0 -- spelled out here */
+	if (!(x > 0.0))
 		return 0;
 	if (x > 65535.0)
 		return 65535;

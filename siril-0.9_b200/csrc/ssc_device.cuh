@@ -19,8 +19,10 @@ __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a,
 __device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
 
 // round_to_WORD, src/core/utils.c:68-74
+// NaN (inf - inf with the coefficients of a frame whose IKSS scale is 0) is undefined in the C source;
+// the reference's x86-64 build yields 0 (cvttsd2si's 0x80000000 truncated to 16 bits), and so does this.
 __device__ __forceinline__ unsigned int round_to_word(double x) {
-	if (x <= 0.0) return 0u;
+	if (!(x > 0.0)) return 0u;
 	if (x > 65535.0) return 65535u;
 	return (unsigned int) __double2int_rz(dadd(x, 0.5));
 }

@@ -138,3 +138,41 @@ def test_cfg3_sigma_full_width_rows_against_oracle(gpu, port):
     one = fr[:1].expand(n, c, h, w).contiguous()
     out1, cnt1, _ = run_pipeline(gpu, one, n, c, h, w, [(0, h)], 2, (4.0, 3.0), 0)
     assert np.array_equal(out1, host_u16(fr[0])) and cnt1[:6].sum() == 0
+
+
+def test_non_finite_coefficients_are_deterministic(gpu):
+    """A frame whose IKSS scale is 0 gets infinite / NaN coefficients (stacking.c:95-121).  Samples
+    normalized to NaN become 0 (what the reference's x86-64 build does), +inf becomes 65535 -- on every
+    kernel path."""
+    import torch
+    dev = torch.device("cuda", 0)
+    sp = torch.cuda.current_stream().cuda_stream
+    raw = np.array([[[[100, 0, 5000, 65535, 7, 8, 9, 10]]], [[[200, 300, 400, 500, 600, 700, 800, 900]]]], dtype=np.uint16)
+    fr = torch.tensor(raw.view(np.int16), device=dev)
+    n, c, h, w = raw.shape
+    cases = [([np.inf, 0.0], [1.0, 1.0], [np.inf, 1.0]), ([np.nan, 0.0], [1.0, 1.0], [np.nan, 1.0]),
+             ([0.0, 0.0], [np.inf, 1.0], [1.0, 1.0])]
+    for off, mul, sc in cases:
+        for norm in (1, 2, 3, 4):
+            if norm in (1, 2):
+                sc = [1.0, 1.0]         # compute_normalization leaves scale at 1.0 in these modes (stacking.c:130-134)
+            with np.errstate(all="ignore"):
+                x = raw[:, 0, 0, :].astype(np.float64)
+                if norm in (1, 3):      # stacking.c:1640-1644
+                    y = x * np.array(sc)[:, None] - np.array(off)[:, None]
+                else:                   # stacking.c:1646-1650
+                    y = (x * np.array(sc)[:, None]) * np.array(mul)[:, None]
+                v = np.where(np.isnan(y) | (y <= 0), 0.0, np.where(y > 65535.0, 65535.0, np.floor(y + 0.5)))
+                expect = np.floor(v.sum(0) / n + 0.5).clip(0, 65535).astype(np.uint16)
+            coeff = torch.tensor(np.array([off, mul, sc], dtype=np.float64), device=dev)
+            for path in (0, 1):
+                gpu.set_kernel_path(path)
+                try:
+                    out = torch.zeros((c, h, w), dtype=torch.int16, device=dev)
+                    cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+                    gpu.dev.stack_mean(gpu.dev.band(fr.data_ptr(), n, c, h, w), out.data_ptr(), cnt.data_ptr(), 0,
+                                       (0.0, 0.0), norm, coeff.data_ptr(), stream=sp)
+                    torch.cuda.synchronize()
+                finally:
+                    gpu.set_kernel_path(0)
+                assert np.array_equal(out.cpu().numpy().view(np.uint16).ravel(), expect), (off, mul, sc, norm, path)

@@ -418,6 +418,38 @@ def test_sigma_register_kernel_gather_variants(gpu, port, w):
         assert np.array_equal(res.data, same["out"]) and np.array_equal(res.irej, same["irej"]), (w, ro)
 
 
+def test_random_shapes_all_kernels(gpu, port):
+    """Seeded sweep over frame counts, image shapes (partial warp tiles, single rows, widths that are / are
+    not multiples of 8), channels, row orders, rejections and normalizations: whatever kernel the
+    dispatcher picks must equal the oracle bit for bit (same sigma form), counters and guard events too.
+    (One of the cases has two-pixel frames with a dead pixel: IKSS scale 0, infinite coefficients, samples
+    normalized to NaN -- which count as 0, as in the reference's x86-64 build.)"""
+    rng = np.random.default_rng(20260101)
+    rej_names = list(REJ)
+    for it in range(48):
+        n = int(rng.choice([2, 3, 5, 8, 15, 16, 17, 31, 32, 33, 63, 64, 65, 90, 128, 130, 257]))
+        c = int(rng.choice([1, 3]))
+        h = int(rng.choice([1, 2, 5, 9]))
+        w = int(rng.choice([2, 6, 8, 14, 16, 24, 34, 40, 64, 66, 72, 130]))
+        if n > 64 and h * w > 400:
+            h = 2
+        norm = int(rng.integers(0, 5))
+        ro = int(rng.integers(0, 2))
+        mode = rej_names[int(rng.integers(0, len(rej_names)))] if rng.random() < 0.85 else "median"
+        fr = synth.make_frames(n, c, h, w, seed=1000 + it, outlier_p=1e-2, zero_p=3e-3, stars=1)
+        seq = gpu.Sequence(fr, row_order=ro)
+        tag = (it, n, c, h, w, norm, ro, mode)
+        if mode == "median":
+            res = gpu.stack_median(seq, normalize=norm, want_coeff=True)
+            assert np.array_equal(res.data, port.stack_median(fr, normalize=norm, coeff=res.coeff, row_order=ro)["out"]), tag
+            continue
+        rj, sig = REJ[mode]
+        res = gpu.stack_mean_with_rejection(seq, rj, sig, norm)
+        same = port.stack_mean(fr, rj, sig, norm, coeff=res.coeff, row_order=ro, sd_mode=port.SD_EXACT)
+        assert np.array_equal(res.data, same["out"]), tag
+        assert np.array_equal(res.irej, same["irej"]) and res.guard_fired == same["guard_fired"], tag
+
+
 def test_fast_normalization_domain_fallback(gpu, port):
     """Coefficients outside the domain of the 2^52 conversion tricks (a nearly black frame against a
     bright reference: mul ~ 5e4, products beyond 2^31) take the conversion-based normalization."""
