@@ -45,9 +45,10 @@ def run_pipeline(gpu, frames_dev, n, c, h, w, bands, rejection, sig, normalize, 
     return host_u16(out), counters.cpu().numpy(), coeff.cpu().numpy()
 
 
+@pytest.mark.parametrize("n", [24, 32, 70])       # block-queue kernel, register sigma kernel (full stack), mid kernel
 @pytest.mark.parametrize("rej,sig", [(2, (4.0, 3.0)), (4, (4.0, 3.0)), (5, (5.0, 2.5))])
-def test_band_decomposition_is_invariant(gpu, port, rej, sig):
-    n, c, h, w = 24, 3, 45, 64
+def test_band_decomposition_is_invariant(gpu, port, rej, sig, n):
+    c, h, w = 3, 45, 64
     fr = synth.make_frames(n, c, h, w, seed=31, outlier_p=5e-3, zero_p=1e-3, stars=4)
     d = dev_u16(fr)
     whole = run_pipeline(gpu, d, n, c, h, w, [(0, h)], rej, sig, 3)
