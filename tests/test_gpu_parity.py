@@ -450,6 +450,41 @@ def test_random_shapes_all_kernels(gpu, port):
         assert np.array_equal(res.irej, same["irej"]) and res.guard_fired == same["guard_fired"], tag
 
 
+def test_random_shapes_frame_walkers_and_shifts(gpu, port):
+    """Seeded sweep over the whole-frame operators (sum, addmax, addmin) and the rejection mean with
+    registration shifts (general kernel): shapes, channels, row orders, shifts larger than the image."""
+    rng = np.random.default_rng(77)
+    for it in range(40):
+        n = int(rng.choice([2, 3, 7, 16, 40, 70]))
+        c = int(rng.choice([1, 3]))
+        h = int(rng.choice([1, 3, 8, 13]))
+        w = int(rng.choice([1, 2, 7, 8, 16, 33, 64]))
+        ro = int(rng.integers(0, 2))
+        big = rng.random() < 0.2
+        sx = rng.integers(-(w + 2) if big else -3, (w + 3) if big else 4, n).astype(np.int32)
+        sy = rng.integers(-(h + 2) if big else -3, (h + 3) if big else 4, n).astype(np.int32)
+        if rng.random() < 0.25:
+            sx = sy = None
+        fr = synth.make_random(n, c, h, w, seed=500 + it, hi=int(rng.choice([300, 5000, 65536])))
+        seq = gpu.Sequence(fr, row_order=ro, shiftx=sx, shifty=sy)
+        tag = (it, n, c, h, w, ro, None if sx is None else sx.tolist(), None if sy is None else sy.tolist())
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            res = gpu.stack_summing(seq)
+            p = port.stack_sum(fr, shiftx=sx, shifty=sy, row_order=ro)
+            assert np.array_equal(res.data, p["out"]) and res.hi == min(p["maxim"], 65535), tag
+        elif kind in (1, 2):
+            res = (gpu.stack_addmax if kind == 1 else gpu.stack_addmin)(seq)
+            p = port.stack_extreme(fr, kind == 1, shiftx=sx, shifty=sy, row_order=ro)
+            assert np.array_equal(res.data, p["out"]) and res.hi == p["hi"], tag
+        else:
+            rj, sig = REJ[list(REJ)[int(rng.integers(0, len(REJ)))]]
+            res = gpu.stack_mean_with_rejection(seq, rj, sig, 0)
+            p = port.stack_mean(fr, rj, sig, 0, shiftx=sx, shifty=sy, row_order=ro, sd_mode=port.SD_EXACT)
+            assert np.array_equal(res.data, p["out"]) and np.array_equal(res.irej, p["irej"]), tag
+            assert res.guard_fired == p["guard_fired"], tag
+
+
 def test_fast_normalization_domain_fallback(gpu, port):
     """Coefficients outside the domain of the 2^52 conversion tricks (a nearly black frame against a
     bright reference: mul ~ 5e4, products beyond 2^31) take the conversion-based normalization."""
