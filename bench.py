@@ -254,6 +254,12 @@ def main():
     hist = torch.zeros((n, pkg.HIST_STRIDE), dtype=torch.int32, device=dev)
     scratch = torch.empty((n, 65536), dtype=torch.int32, device=dev)
     stats = torch.empty((4, n), dtype=torch.float64, device=dev)
+    shard_stats = world > 1 and n % world == 0              # reduce-scatter the histograms, IKSS on n / world frames per rank
+    n_loc = n // world if shard_stats else n
+    if shard_stats:
+        hist_loc = torch.empty((n_loc, pkg.HIST_STRIDE), dtype=torch.int32, device=dev)
+        stats_loc = torch.empty((4, n_loc), dtype=torch.float64, device=dev)
+        stats_all = torch.empty((world, 4, n_loc), dtype=torch.float64, device=dev)
     coeff = torch.empty((3, n), dtype=torch.float64, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     counters = torch.zeros(pkg.N_COUNTERS, dtype=torch.int64, device=dev)
@@ -265,10 +271,20 @@ def main():
         counters.zero_()
         if ev: ev[0].record(stream)
         pkg.dev.histogram(band, hist.data_ptr(), sp)
-        if world > 1:
-            dist.all_reduce(hist)                           # exact integer SUM over the row bands (NCCL)
-        if ev: ev[1].record(stream)
-        pkg.dev.ikss(hist.data_ptr(), n, stats.data_ptr(), scratch.data_ptr(), sp)
+        if world > 1 and shard_stats:
+            # exact integer SUM over the row bands, each rank receiving the summed histograms of ITS frames
+            # only (half the traffic of an all-reduce); it runs the IKSS for those, then the per-frame
+            # statistics (4 doubles each) are gathered: every rank ends up with identical coefficients
+            dist.reduce_scatter_tensor(hist_loc.view(-1), hist.view(-1))
+            if ev: ev[1].record(stream)
+            pkg.dev.ikss(hist_loc.data_ptr(), n_loc, stats_loc.data_ptr(), scratch.data_ptr(), sp)
+            dist.all_gather_into_tensor(stats_all.view(-1), stats_loc.view(-1))
+            stats.copy_(stats_all.view(world, 4, n_loc).permute(1, 0, 2).reshape(4, n))
+        else:
+            if world > 1:
+                dist.all_reduce(hist)                       # exact integer SUM over the row bands (NCCL)
+            if ev: ev[1].record(stream)
+            pkg.dev.ikss(hist.data_ptr(), n, stats.data_ptr(), scratch.data_ptr(), sp)
         pkg.dev.norm_coeffs(stats.data_ptr(), n, 0, CFG["normalize"], coeff.data_ptr(), status.data_ptr(), sp)
         if ev: ev[2].record(stream)
         pkg.dev.stack_mean(band, out.data_ptr(), counters.data_ptr(), CFG["rejection"], CFG["sig"],
