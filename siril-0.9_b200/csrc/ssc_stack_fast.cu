@@ -67,14 +67,15 @@ enum { MODE_MEDIAN = 0, MODE_NOREJ = 1, MODE_SIGMA_REG = 2, MODE_QUEUE = 3 };
 template <int NP, int KIND, bool FULL>
 __device__ __forceinline__ void normalize_staged(unsigned int *stage_t, int stride, const double *s_coef, int N,
 		unsigned int &Sa, unsigned int &Sb, unsigned long long &Qa, unsigned long long &Qb) {
-	static_assert(NP % 4 == 0, "groups of four frames");
+	constexpr int G = 8;	// frames per round
+	static_assert(NP % G == 0, "groups of G frames");
 #pragma unroll 1
-	for (int f0 = 0; f0 < (FULL ? NP : N); f0 += 4) {
+	for (int f0 = 0; f0 < (FULL ? NP : N); f0 += G) {
 		// all loads of a group first: the coefficient loads are off the critical path of the FP64 chain
-		unsigned int w[4];
-		double off[4], mul[4], sc[4];
+		unsigned int w[G];
+		double off[G], mul[G], sc[G];
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
+		for (int j = 0; j < G; j++) {
 			w[j] = stage_t[(f0 + j) * stride];
 			off[j] = 0.0; mul[j] = 1.0; sc[j] = 1.0;
 			if constexpr (KIND == ADDITIVE || KIND == ADDITIVE_SCALING) off[j] = s_coef[f0 + j];
@@ -82,7 +83,7 @@ __device__ __forceinline__ void normalize_staged(unsigned int *stage_t, int stri
 			if constexpr (KIND == ADDITIVE_SCALING || KIND == MULTIPLICATIVE_SCALING) sc[j] = s_coef[128 + f0 + j];
 		}
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
+		for (int j = 0; j < G; j++) {
 			if (!FULL && f0 + j >= N) break;	// (the words behind the N samples hold the 0xFFFF sentinels)
 			if constexpr (KIND != NO_NORM) {
 				w[j] = normalize_pair_fast<KIND>(w[j], off[j], mul[j], sc[j], Qa, Qb);
