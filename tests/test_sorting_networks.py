@@ -123,3 +123,44 @@ def test_mid_kernel_merge_schedule_sorts(n, npad):
         out = mid_kernel_schedule(col, n, npad, net64)
         assert np.array_equal(out[:n], np.sort(col))
         assert (out[n:] == 0xFFFF).all()
+
+
+def test_single_precision_no_rejection_proof_is_conservative():
+    """ssc_stack_fast.cu:clip_cannot_fire decides "the first sigma-clipping pass rejects nothing" in FP32;
+    it must never say so when the exact FP64 test (M2 - 2 min > floor(2 sig_low sigma), likewise above)
+    would reject.  Restated in numpy on random and on adversarial columns (extremes placed right at the
+    threshold); the GPU's approximate square root is covered by widening the FP32 estimate by 4 ulp."""
+    rng = np.random.default_rng(5)
+    n = 64
+    sig_low, sig_high = 4.0, 3.0
+    cols = []
+    base = rng.normal(3000, 40, size=(200000, n))
+    cols.append(base)
+    for k in (2.4, 2.9, 3.0, 3.05, 3.9, 4.0, 4.05):                 # push one sample to about k sigma
+        c = rng.normal(20000, 300, size=(60000, n))
+        c[:, 0] = 20000 + k * 300 * rng.normal(1.0, 0.01, size=60000)
+        cols.append(c)
+        c = c.copy()
+        c[:, 0] = 20000 - k * 300 * rng.normal(1.0, 0.01, size=60000)
+        cols.append(c)
+    cols.append(np.full((10, n), 65535.0))
+    cols.append(rng.integers(0, 2, size=(1000, n)).astype(float) * 65535)
+    x = np.clip(np.rint(np.concatenate(cols)), 0, 65535).astype(np.int64)
+    x.sort(axis=1)
+    S, Q = x.sum(1), (x * x).sum(1)
+    D = n * Q - S * S
+    M2 = x[:, n // 2 - 1] + x[:, n // 2]
+    d_lo, d_hi = M2 - 2 * x[:, 0], 2 * x[:, -1] - M2
+    # exact path (ssc_device.cuh:sd_from_sums + the integer thresholds of the queue pass)
+    sigma = np.sqrt((D.astype(np.float64) / float(n * n)) * (float(n) / float(n - 1)))
+    TL = np.floor(np.minimum(2.0 * (sig_low * sigma), 1073741824.0))
+    TH = np.floor(np.minimum(2.0 * (sig_high * sigma), 1073741824.0))
+    rejects = (d_lo > TL) | (d_hi > TH)
+    # FP32 proof, with the square root 4 ulp too LARGE (the worst direction for the proof)
+    f32 = np.float32
+    s32 = np.sqrt(D.astype(f32) * f32(1.0 / (n * (n - 1)))).astype(f32) * f32(1.0 + 4 * 2.0 ** -23)
+    t_lo = f32(2.0) * f32(sig_low) * s32 * f32(0.9999) - f32(1.0)
+    t_hi = f32(2.0) * f32(sig_high) * s32 * f32(0.9999) - f32(1.0)
+    clear = ((d_lo == 0) | (d_lo.astype(f32) < t_lo)) & ((d_hi == 0) | (d_hi.astype(f32) < t_hi))
+    assert not (clear & rejects).any()
+    assert clear.mean() > 0.3 and rejects.mean() > 0.1              # the sweep exercises both outcomes
