@@ -751,15 +751,18 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 			: (total + FAST_THREADS - 1) / FAST_THREADS;
 	if (tiles > 0x7FFFFFFFull) return SSC_ERR_ARG;
 	unsigned long long blocks = tiles;
-	{	// a bounded grid of looping blocks: 4 per resident slot measured best (SSC_FAST_WAVES overrides)
+	{	// a bounded grid of looping blocks: 8 per resident slot for big launches, 4 for small ones (measured;
+		// a block should keep a few dozen tiles to amortise its prologue).  SSC_FAST_WAVES overrides.
 		int dev = 0, sms = 148, per_sm = 1;
 		cudaGetDevice(&dev);
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stack_fast<NP, FULL, MODE, ROWTILE>, FAST_THREADS, smem) != cudaSuccess || per_sm < 1)
 			per_sm = 1;
-		static int waves = 0;
-		if (!waves) { const char *e = getenv("SSC_FAST_WAVES"); waves = e ? atoi(e) : 4; if (waves < 1) waves = 1; }
-		const unsigned long long cap = (unsigned long long) sms * per_sm * waves;
+		static int forced = -1;
+		if (forced < 0) { const char *e = getenv("SSC_FAST_WAVES"); forced = e ? atoi(e) : 0; if (forced < 0) forced = 0; }
+		const unsigned long long slots = (unsigned long long) sms * per_sm;
+		const int waves = forced ? forced : (tiles / slots >= 256 ? 8 : 4);
+		const unsigned long long cap = slots * waves;
 		if (blocks > cap) blocks = cap;
 	}
 	LeftoverList list{nullptr, 0, nullptr};
