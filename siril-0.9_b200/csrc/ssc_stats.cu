@@ -133,19 +133,23 @@ k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
 			q[k] = nxt < v_end ? __ldg(v4 + nxt) : make_uint4(0, 0, 0, 0);
 			if (idx < v_end) count8(v);
 		}
-		// Samples this CTA has put into the full table since its last flush.  Two monotonic
-		// counters used alternately: a warp already in group g+1 adds to the other one, so every
-		// thread reads the same value here and the flush decision is block-uniform.
-		const unsigned int w_out = __reduce_add_sync(0xffffffffu, outside);
-		outside = 0;
-		if (lane == 0 && w_out) atomicAdd(&s_outside[g & 1], w_out);
-		__syncthreads();
-		const unsigned int t = s_outside[g & 1];
-		in_full += t - prev[g & 1];
-		prev[g & 1] = t;
-		if (in_full + HIST_GROUP_SAMPLES + 16 > 65535u) {	// the next group could overflow a counter
-			flush_full();
-			in_full = 0;
+		// Samples this CTA has put into the full table since its last flush, checked every second group
+		// (a barrier each time).  Two monotonic counters used alternately: a warp already in the next
+		// round adds to the other one, so every thread reads the same value here and the flush decision
+		// is block-uniform.
+		if ((g & 1) == 1 || g + 1 == n_groups) {
+			const unsigned int round = (unsigned int) (g >> 1) & 1u;
+			const unsigned int w_out = __reduce_add_sync(0xffffffffu, outside);
+			outside = 0;
+			if (lane == 0 && w_out) atomicAdd(&s_outside[round], w_out);
+			__syncthreads();
+			const unsigned int t = s_outside[round];
+			in_full += t - prev[round];
+			prev[round] = t;
+			if (in_full + 2 * HIST_GROUP_SAMPLES + 16 > 65535u) {	// the next two groups could overflow a counter
+				flush_full();
+				in_full = 0;
+			}
 		}
 	}
 	if (part == 0) {	// the few (< 16) samples outside the vectors
