@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -28,7 +29,7 @@ struct Bound {
 	std::vector<double> exposure;
 	bool have_reg = false;
 };
-std::map<const void *, Bound> g_bound;
+std::map<const void *, std::shared_ptr<const Bound>> g_bound;	// a running operator keeps its own reference
 ssc_callbacks g_cb = {nullptr, nullptr, nullptr};
 ssc_result g_result;
 bool g_has_result = false;
@@ -47,21 +48,29 @@ int fail(int code, const char *fmt, ...) {
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
 	return fail(SSC_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 
+ssc_callbacks callbacks() {	// a snapshot: ssc_set_callbacks may run on another thread
+	std::lock_guard<std::mutex> lk(g_mu);
+	return g_cb;
+}
+
 void log_msg(const char *fmt, ...) {
 	char buf[512];
 	va_list ap;
 	va_start(ap, fmt);
 	vsnprintf(buf, sizeof(buf), fmt, ap);
 	va_end(ap);
-	if (g_cb.log) g_cb.log(buf);
+	const ssc_callbacks cb = callbacks();
+	if (cb.log) cb.log(buf);
 }
 
 void progress(const char *text, double frac) {
-	if (g_cb.progress) g_cb.progress(text, frac);
+	const ssc_callbacks cb = callbacks();
+	if (cb.progress) cb.progress(text, frac);
 }
 
 bool keep_running() {
-	return g_cb.should_continue ? g_cb.should_continue() != 0 : true;
+	const ssc_callbacks cb = callbacks();
+	return cb.should_continue ? cb.should_continue() != 0 : true;
 }
 
 int check_band(const ssc_band *b) {
@@ -199,7 +208,8 @@ int ssc_bind_sequence(const sequence *seq, const ssc_sequence_view *view) {
 	if (!seq || !view || !view->frames) return fail(SSC_ERR_ARG, "null sequence view");
 	if (view->number < 1 || view->rx < 1 || view->ry < 1 || (view->nb_layers != 1 && view->nb_layers != 3))
 		return fail(SSC_ERR_ARG, "bad sequence geometry");
-	Bound b;
+	auto bp = std::make_shared<Bound>();
+	Bound &b = *bp;
 	b.view = *view;
 	b.frames.assign(view->frames, view->frames + view->number);
 	b.have_reg = view->shiftx || view->shifty;
@@ -211,7 +221,7 @@ int ssc_bind_sequence(const sequence *seq, const ssc_sequence_view *view) {
 	}
 	if (view->exposure) b.exposure.assign(view->exposure, view->exposure + view->number);
 	std::lock_guard<std::mutex> lk(g_mu);
-	g_bound[seq] = std::move(b);
+	g_bound[seq] = std::move(bp);
 	return SSC_OK;
 }
 
@@ -228,8 +238,11 @@ void ssc_set_callbacks(const ssc_callbacks *cb) {
 int ssc_set_devices(const int *device_ids, int count) {
 	int n = ssc_device_count();
 	if (count < 1 || !device_ids) return fail(SSC_ERR_ARG, "empty device list");
-	for (int i = 0; i < count; i++)
+	for (int i = 0; i < count; i++) {
 		if (device_ids[i] < 0 || device_ids[i] >= n) return fail(SSC_ERR_CUDA, "device %d not present", device_ids[i]);
+		for (int j = 0; j < i; j++)	// the per-device workspace is keyed by device id: one band per device
+			if (device_ids[j] == device_ids[i]) return fail(SSC_ERR_ARG, "device %d listed twice", device_ids[i]);
+	}
 	std::lock_guard<std::mutex> lk(g_mu);
 	g_devices.assign(device_ids, device_ids + count);
 	return SSC_OK;
@@ -258,7 +271,7 @@ inline bool frame_walker(OpKind op) { return op == OP_SUM || op == OP_ADDMAX || 
 
 struct Job {
 	OpKind op;
-	const Bound *seq;
+	std::shared_ptr<const Bound> seq;	// stays alive through unbind / re-bind on another thread
 	std::vector<int> images;	// sequence image index per stack position
 	int normalize = NO_NORM, rejection = NO_REJEC;
 	double sig[2] = {0, 0};
@@ -410,9 +423,24 @@ int run_job(const Job &job) {
 			if (it != g_cache.end()) free_b += it->second.frames.cap + it->second.out.cap + it->second.hist.cap
 					+ it->second.scratch.cap + it->second.acc.cap;
 		}
-		const size_t fixed = (size_t) N * (SSC_HIST_STRIDE + 65536) * 4 + (64u << 20);
-		const size_t budget = free_b > fixed ? (size_t) ((free_b - fixed) * 0.85) : 0;
-		const size_t per_row = (size_t) N * C * W * sizeof(WORD) + (size_t) C * W * (sizeof(WORD) + sizeof(uint32_t));
+		// what the library itself keeps on the device besides frames and result: histograms and IKSS scratch,
+		// the linear fit's spill area (ssc_stack_mid.cu), 4 bytes per result pixel for the sigma kernel's
+		// hand-back list, and the extra source rows the y shifts reach for (source_rows())
+		size_t fixed = (size_t) N * (SSC_HIST_STRIDE + 65536) * 4 + (64u << 20);
+		if (job.op == OP_MEAN && job.rejection == LINEARFIT) fixed += ssc::spill_bytes_wanted();
+		int reach = 0;
+		if (job.op != OP_MEDIAN && job.seq->have_reg) {
+			int lo = 0, hi = 0;
+			for (int idx : job.images) { lo = std::min(lo, job.seq->sy[idx]); hi = std::max(hi, job.seq->sy[idx]); }
+			reach = hi - lo;
+		}
+		fixed += (size_t) reach * N * C * W * sizeof(WORD);
+		size_t budget = free_b > fixed ? (size_t) ((free_b - fixed) * 0.85) : 0;
+		if (const char *e = getenv("SSC_HBM_BUDGET_BYTES")) {	// tests force the row split with it
+			const unsigned long long cap = strtoull(e, nullptr, 10);
+			if (cap > 0 && cap < budget) budget = (size_t) cap;
+		}
+		const size_t per_row = (size_t) N * C * W * sizeof(WORD) + (size_t) C * W * (sizeof(WORD) + 2 * sizeof(uint32_t));
 		size_t fit_rows = per_row ? budget / per_row : 0;
 		if (fit_rows < 1) return fail(SSC_ERR_GENERIC, "not enough device memory for one row of %d frames", N);
 		const int n_pieces = (int) ((rows + fit_rows - 1) / fit_rows);
@@ -761,7 +789,7 @@ int make_job(struct stacking_args *args, OpKind op, Job &job) {
 		std::lock_guard<std::mutex> lk(g_mu);
 		auto it = g_bound.find(args->seq);
 		if (it == g_bound.end()) return fail(SSC_ERR_UNBOUND, "sequence not bound (ssc_bind_sequence)");
-		job.seq = &it->second;
+		job.seq = it->second;
 	}
 	job.op = op;
 	const int number = job.seq->view.number;
@@ -787,7 +815,11 @@ int make_job(struct stacking_args *args, OpKind op, Job &job) {
 			job.images.push_back(idx);
 		}
 		job.normalize = args->normalize;
-		if (job.normalize < NO_NORM || job.normalize > MULTIPLICATIVE_SCALING) job.normalize = ADDITIVE_SCALING;	// "default:" label
+		if (job.normalize < NO_NORM || job.normalize > MULTIPLICATIVE_SCALING)
+			// the "default:" labels: stack_median groups it with the additive branch (stacking.c:753-757),
+			// stack_mean_with_rejection with NO_NORM (:1636-1638: raw samples, whatever coefficients
+			// compute_normalization's own default: label produced)
+			job.normalize = op == OP_MEAN ? NO_NORM : ADDITIVE_SCALING;
 		if (op == OP_MEAN) {
 			job.rejection = args->type_of_rejection;
 			if (job.rejection < NO_REJEC || job.rejection > LINEARFIT) job.rejection = NO_REJEC;	// "default:" label
@@ -874,7 +906,7 @@ int ssc_compute_normalization(struct stacking_args *args, norm_coeff *coeff, nor
 	int rc = make_job(args, OP_MEAN, job);
 	if (rc) return rc == SSC_ERR_GENERIC ? 1 : rc;
 	const int N = (int) job.images.size();
-	job.normalize = mode;
+	job.normalize = (mode < NO_NORM || mode > MULTIPLICATIVE_SCALING) ? ADDITIVE_SCALING : mode;	// "default:" label, :96
 	job.want_coeff_only = true;
 	std::vector<double> c((size_t) 3 * N);
 	job.coeff_out = c.data();

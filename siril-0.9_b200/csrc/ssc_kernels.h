@@ -41,6 +41,7 @@ int launch_stack_fast(const StackParams &p, int is_median, cudaStream_t stream);
 bool mid_path_eligible(const StackParams &p, int is_median);
 int launch_stack_mid(const StackParams &p, int is_median, cudaStream_t stream);
 void release_mid_scratch(int dev);
+size_t spill_bytes_wanted();	// size of the linear fit's spill area (SSC_SPILL_BYTES overrides the 1 GB default)
 // picks the register-network kernel when the shape allows it, the general kernel otherwise
 int launch_stack(const StackParams &p, int is_median, cudaStream_t stream);
 void release_kernel_scratch(int dev);	// per-device lists and tables the kernels keep between launches

@@ -12,6 +12,7 @@
 // the rare history-dependent pixels back to this one.
 #include "ssc_column.cuh"
 #include "ssc_kernels.h"
+#include <mutex>
 #include "ssc_leftover.cuh"
 
 namespace ssc {
@@ -200,7 +201,19 @@ void release_kernel_scratch(int dev) {
 
 int g_kernel_path = 0;
 
-int launch_stack(const StackParams &p_in, int is_median, cudaStream_t stream) {
+// The kernels' per-device scratch (sigma hand-back list, linear-fit spill area and tables) is shared by
+// every launch on a device.  Launches are therefore chained: the host side runs under a per-device
+// mutex and a launch on another stream than the previous one first waits for that launch's event, so two
+// streams or two host threads can never see each other's hand-back list or spilled columns.
+struct ScratchOwner {
+	std::mutex mu;
+	cudaEvent_t done = nullptr;
+	cudaStream_t last = nullptr;
+	bool any = false;
+};
+static ScratchOwner g_scratch_owner[64];
+
+static int launch_stack_unchained(const StackParams &p_in, int is_median, cudaStream_t stream) {
 	StackParams p = p_in;
 	p.fit = FitTables{nullptr, nullptr, nullptr, 0};
 	if (!is_median && p.rejection == LINEARFIT) {
@@ -213,6 +226,21 @@ int launch_stack(const StackParams &p_in, int is_median, cudaStream_t stream) {
 	if (g_kernel_path != 1 && mid_path_eligible(p, is_median))
 		return launch_stack_mid(p, is_median, stream);
 	return launch_stack_generic(p, nullptr, nullptr, 0, is_median, stream);
+}
+
+int launch_stack(const StackParams &p, int is_median, cudaStream_t stream) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) return SSC_ERR_ARG;
+	ScratchOwner &own = g_scratch_owner[dev];
+	std::lock_guard<std::mutex> lk(own.mu);
+	if (!own.done && cudaEventCreateWithFlags(&own.done, cudaEventDisableTiming) != cudaSuccess) return SSC_ERR_CUDA;
+	if (own.any && own.last != stream && cudaStreamWaitEvent(stream, own.done, 0) != cudaSuccess) return SSC_ERR_CUDA;
+	const int rc = launch_stack_unchained(p, is_median, stream);
+	if (cudaEventRecord(own.done, stream) != cudaSuccess) return rc ? rc : SSC_ERR_CUDA;
+	own.last = stream;
+	own.any = true;
+	return rc;
 }
 
 }  // namespace ssc

@@ -344,6 +344,14 @@ struct SpillStore {
 static SpillStore g_spill_store[64];
 constexpr size_t SPILL_BYTES = (size_t) 1 << 30;	// columns of one row slice
 
+size_t spill_bytes_wanted() {
+	if (const char *e = getenv("SSC_SPILL_BYTES")) {	// tests force several slices with a small area
+		const long long v = atoll(e);
+		if (v > 0) return (size_t) v;
+	}
+	return SPILL_BYTES;
+}
+
 void release_mid_scratch(int dev) {
 	if (dev < 0 || dev >= 64) return;
 	if (g_spill_store[dev].mem) cudaFree(g_spill_store[dev].mem);
@@ -401,11 +409,7 @@ static int launch_mid(const StackParams &p, int is_median, cudaStream_t stream) 
 	const size_t px_per_row = (size_t) b.layers * b.width;	// a slice takes the same rows of every layer
 	// (tiles run over layers x rows x pairs, so a slice is a range of rows of ONE launch only when it
 	// covers whole rows of all layers: slices are bands with fewer out_rows)
-	size_t spill_bytes = SPILL_BYTES;
-	if (const char *e = getenv("SSC_SPILL_BYTES")) {	// tests force several slices with a small area
-		const long long v = atoll(e);
-		if (v > 0) spill_bytes = (size_t) v;
-	}
+	const size_t spill_bytes = spill_bytes_wanted();
 	size_t rows_per_slice = spill_bytes / (per_px * px_per_row + 1);
 	if (rows_per_slice < 1) rows_per_slice = 1;
 	if (rows_per_slice > (size_t) b.out_rows) rows_per_slice = (size_t) b.out_rows;

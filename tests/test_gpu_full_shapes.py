@@ -1,0 +1,204 @@
+"""BASELINE.json's remaining shapes at their real widths and frame counts (cfg4: 200 x 4656 wide,
+winsorized, additive+scale; cfg5: 1000 x 1936 wide SER, linear fit), the histogram kernel on
+wide-range data at sizes where its mid-stream flush fires, and the normalization statistics of a
+full 24 Mpx frame against the reference's own sort-based statistics().
+
+Checked against the oracle restatement (same sigma / fit formulation: bit-exact; the reference's
+formulation: +-1 ADU on <= 0.01 % of the pixels, equal counters) and, on a few rows, against the
+reference's unmodified stacking.c (oracle/_ref)."""
+import numpy as np
+import pytest
+
+import synth
+from test_gpu_device_layer import dev_u16, host_u16, run_pipeline
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+SEED = 0x5349524C
+
+
+def close_enough(a, b, frac=1e-4):
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    return d.max() <= 1 and (d != 0).sum() <= max(1, int(frac * d.size))
+
+
+def synth_band(gpu, n, c, rows, w, row0, full_h, kind):
+    sp = torch.cuda.current_stream().cuda_stream
+    fr = torch.empty((n, c, rows, w), dtype=torch.int16, device="cuda")
+    gpu.dev.synth_frames(fr.data_ptr(), n, c, rows, w, 0, row0, full_h, kind, SEED, sp)
+    torch.cuda.synchronize()
+    return fr
+
+
+# --------------------------------------------------------------------------------------------- cfg4
+def test_cfg4_winsorized_full_width_rows(gpu, port, refrun):
+    """configs[3] per row: 200 mono frames, 4656 px wide, winsorized 4/3, additive+scale (the mid
+    kernel's <256, 64> instantiation with its real tile/row geometry)."""
+    n, c, h, w = 200, 1, 24, 4656
+    fr = synth_band(gpu, n, c, h, w, 1700, 3520, 0)
+    out, counters, coeff = run_pipeline(gpu, fr, n, c, h, w, [(0, h)], 4, (4.0, 3.0), 3)
+    rows = list(range(0, h, 3))                                        # 8 full rows
+    sub = host_u16(fr[:, :, rows, :].contiguous())
+    same = port.stack_mean(sub, 4, (4.0, 3.0), 3, coeff=coeff, sd_mode=port.SD_EXACT)
+    assert np.array_equal(out[:, rows, :], same["out"])
+    assert counters[6] == same["guard_fired"] == 0 and counters[7] == 0
+    gsl = port.stack_mean(sub, 4, (4.0, 3.0), 3, coeff=coeff, sd_mode=port.SD_GSL)
+    assert close_enough(out[:, rows, :], gsl["out"])
+    assert np.array_equal(same["irej"], gsl["irej"])
+    # all rows' counters: the whole slab through the oracle in the kernel's sigma formulation
+    whole = port.stack_mean(host_u16(fr), 4, (4.0, 3.0), 3, coeff=coeff, sd_mode=port.SD_EXACT)
+    assert np.array_equal(out, whole["out"])
+    assert np.array_equal(counters[:6].reshape(3, 2), whole["irej"].astype(np.int64))
+    # the reference itself on two rows (it computes its own statistics from those rows, so the GPU
+    # pipeline runs on exactly those rows as well)
+    two = fr[:, :, 10:12, :].contiguous()
+    out2, cnt2, coeff2 = run_pipeline(gpu, two, n, c, 2, w, [(0, 2)], 4, (4.0, 3.0), 3)
+    ref = refrun.run(host_u16(two), refrun.MEAN, 4, 3, (4.0, 3.0), want_coeff=True)
+    assert ref["retval"] == 0
+    assert np.allclose(coeff2, ref["coeff"], rtol=1e-11, atol=1e-9)
+    assert close_enough(out2, ref["out"])
+    assert np.array_equal(cnt2[:6].reshape(3, 2), ref["irej"].astype(np.int64))
+
+
+def test_cfg4_median_and_sigma_full_width_rows(gpu, port):
+    """The same shape through the other modes of the mid kernel."""
+    n, c, h, w = 200, 1, 6, 4656
+    fr = synth_band(gpu, n, c, h, w, 900, 3520, 0)
+    host = host_u16(fr)
+    out, _, _ = run_pipeline(gpu, fr, n, c, h, w, [(0, h)], 0, (0, 0), 0, median=True)
+    assert np.array_equal(out, port.stack_median(host)["out"])
+    for rej, sig in ((2, (4.0, 3.0)), (1, (0.2, 0.1)), (3, (4.0, 3.0))):
+        out, counters, coeff = run_pipeline(gpu, fr, n, c, h, w, [(0, h)], rej, sig, 4)
+        same = port.stack_mean(host, rej, sig, 4, coeff=coeff, sd_mode=port.SD_EXACT)
+        assert np.array_equal(out, same["out"]), rej
+        assert np.array_equal(counters[:6].reshape(3, 2), same["irej"].astype(np.int64)), rej
+
+
+# --------------------------------------------------------------------------------------------- cfg5
+def test_cfg5_linear_fit_full_width_rows(gpu, port, refrun):
+    """configs[4] per row: 1000 mono SER frames (planetary disc), 1936 px wide, linear fit 5/2.5, no
+    normalization, default spill area; the slab crosses the disc's limb and centre."""
+    n, c, h, w = 1000, 1, 16, 1936
+    fr = synth_band(gpu, n, c, h, w, 600, 1216, 1)
+    sp = torch.cuda.current_stream().cuda_stream
+    out = torch.zeros((c, h, w), dtype=torch.int16, device="cuda")
+    cnt = torch.zeros(gpu.N_COUNTERS, dtype=torch.int64, device="cuda")
+    band = gpu.dev.band(fr.data_ptr(), n, c, h, w, row_order=gpu.ROWS_SER)
+    gpu.dev.stack_mean(band, out.data_ptr(), cnt.data_ptr(), 5, (5.0, 2.5), 0, None, stream=sp)
+    torch.cuda.synchronize()
+    got, counters = host_u16(out), cnt.cpu().numpy()
+    host = host_u16(fr)
+    same = port.stack_mean(host, 5, (5.0, 2.5), 0, row_order=1, sd_mode=port.SD_EXACT)
+    d = got.astype(np.int32) - same["out"].astype(np.int32)
+    assert np.abs(d).max() <= 1 and (d != 0).mean() <= 1e-4            # the bar of BASELINE.json
+    assert np.array_equal(counters[:6].reshape(3, 2), same["irej"].astype(np.int64))
+    assert counters[6] == same["guard_fired"] and counters[7] == 0
+    # the reference itself (stacking.c:1750-1784 + gsl_fit_linear) on two rows
+    two = fr[:, :, 7:9, :].contiguous()
+    out2 = torch.zeros((c, 2, w), dtype=torch.int16, device="cuda")
+    cnt.zero_()
+    gpu.dev.stack_mean(gpu.dev.band(two.data_ptr(), n, c, 2, w, row_order=gpu.ROWS_SER), out2.data_ptr(),
+                       cnt.data_ptr(), 5, (5.0, 2.5), 0, None, stream=sp)
+    torch.cuda.synchronize()
+    ref = refrun.run(host_u16(two), refrun.MEAN, 5, 0, (5.0, 2.5), row_order=1)
+    assert ref["retval"] == 0
+    assert close_enough(host_u16(out2), ref["out"])
+    if cnt[6].item() == 0:
+        assert np.array_equal(cnt[:6].cpu().numpy().reshape(3, 2), ref["irej"].astype(np.int64))
+
+
+def test_cfg5_linear_fit_whole_image_slices(gpu, port):
+    """The whole 1000 x 1936x1216 stack (4.7 GB) on one GPU: several spill slices at the default 1 GB
+    area; sampled rows against the oracle, and the 8-band decomposition (one band per GPU of the named
+    configuration) gives the same image and counters."""
+    n, c, h, w = 1000, 1, 1216, 1936
+    fr = synth_band(gpu, n, c, h, w, 0, h, 1)
+    sp = torch.cuda.current_stream().cuda_stream
+    out = torch.zeros((c, h, w), dtype=torch.int16, device="cuda")
+    cnt = torch.zeros(gpu.N_COUNTERS, dtype=torch.int64, device="cuda")
+    gpu.dev.stack_mean(gpu.dev.band(fr.data_ptr(), n, c, h, w, row_order=gpu.ROWS_SER), out.data_ptr(),
+                       cnt.data_ptr(), 5, (5.0, 2.5), 0, None, stream=sp)
+    torch.cuda.synchronize()
+    out_b = torch.zeros((c, h, w), dtype=torch.int16, device="cuda")
+    cnt_b = torch.zeros(gpu.N_COUNTERS, dtype=torch.int64, device="cuda")
+    for g in range(8):
+        gpu.dev.stack_mean(gpu.dev.band(fr.data_ptr(), n, c, h, w, out_row0=152 * g, out_rows=152,
+                                        row_order=gpu.ROWS_SER), out_b.data_ptr(), cnt_b.data_ptr(), 5, (5.0, 2.5), 0,
+                           None, out_layer_stride=h * w, out_buf_row0=0, stream=sp)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out_b) and torch.equal(cnt, cnt_b)
+    # result row R comes from storage row H-1-R (SER); replay 6 result rows spread over the slices
+    rows = [0, 199, 607, 608, 1000, 1215]
+    src = [h - 1 - r for r in rows]
+    sub = host_u16(fr[:, :, src, :].contiguous())                      # as a FITS-ordered mini image
+    same = port.stack_mean(sub, 5, (5.0, 2.5), 0, sd_mode=port.SD_EXACT)
+    got = host_u16(out)[:, rows, :]
+    d = got.astype(np.int32) - same["out"].astype(np.int32)
+    assert np.abs(d).max() <= 1 and (d != 0).mean() <= 1e-4
+
+
+# ------------------------------------------------------------------------- K4 on wide-range data
+def test_histogram_wide_range_flushes_mid_stream(gpu, port, refrun):
+    """k_histogram's packed 16-bit table must be flushed mid-stream once a CTA has put ~16 k samples
+    outside its 32-bit window (ssc_stats.cu flush_full / s_outside[]): uniform-random u16, a range
+    wider than the window, and a planetary disc, at 16 Mpx per frame (>100 k samples per CTA).  Every
+    bin is compared with the oracle's histogram, the statistics with the reference's statistics()."""
+    h = w = 4096
+    rng = np.random.default_rng(77)
+    fr = np.empty((4, 1, h, w), np.uint16)
+    fr[0, 0] = rng.integers(0, 65536, (h, w), dtype=np.int64)
+    fr[1, 0] = rng.integers(0, 6000, (h, w), dtype=np.int64)           # 3x the window: partly inside
+    fr[2, 0] = np.where(rng.random((h, w)) < 0.5, 40000, rng.integers(0, 65536, (h, w), dtype=np.int64))
+    d = dev_u16(fr)
+    sp = torch.cuda.current_stream().cuda_stream
+    gpu.dev.synth_frames(d[3:].data_ptr(), 1, 1, h, w, 0, 0, h, 1, SEED, sp)      # planetary disc
+    torch.cuda.synchronize()
+    fr[3] = host_u16(d[3])
+    n = 4
+    hist = torch.zeros((n, gpu.HIST_STRIDE), dtype=torch.int32, device="cuda")
+    scratch = torch.empty((n, 65536), dtype=torch.int32, device="cuda")
+    stats = torch.empty((4, n), dtype=torch.float64, device="cuda")
+    gpu.dev.histogram(gpu.dev.band(d.data_ptr(), n, 1, h, w), hist.data_ptr(), sp)
+    gpu.dev.ikss(hist.data_ptr(), n, stats.data_ptr(), scratch.data_ptr(), sp)
+    torch.cuda.synchronize()
+    got = hist.cpu().numpy().view(np.uint32)
+    st = stats.cpu().numpy()
+    for f in range(n):
+        expect, mx = port.histogram(fr[f])
+        assert np.array_equal(got[f, :65536], expect), f
+        assert got[f, :65536].sum() == h * w
+        loc, sc, nv, ng = refrun.frame_stats(fr[f])
+        assert st[0, f] == loc, f                                      # a bin value: exact
+        assert abs(st[1, f] - sc) <= 1e-11 * abs(sc), f
+        assert st[2, f] == nv and st[3, f] == ng
+    # band decomposition at this size: three uneven bands add up to the same histograms
+    hist2 = torch.zeros_like(hist)
+    for r0, rn in ((0, 1000), (1000, 3000), (4000, 96)):
+        gpu.dev.histogram(gpu.dev.band(d.data_ptr(), n, 1, h, w, out_row0=r0, out_rows=rn), hist2.data_ptr(), sp)
+    torch.cuda.synchronize()
+    assert torch.equal(hist[:, :65536], hist2[:, :65536])
+
+
+def test_cfg3_frame_statistics_full_size(gpu, refrun):
+    """Location / scale of full 6000x4000 RGB frames of configs[2] against the reference's sort-based
+    statistics() (statistics.c:277-290): location exact, scale within 1e-11 relative; and the
+    coefficients that follow."""
+    n, c, h, w = 2, 3, 4000, 6000
+    fr = synth_band(gpu, n, c, h, w, 0, h, 0)
+    sp = torch.cuda.current_stream().cuda_stream
+    hist = torch.zeros((n, gpu.HIST_STRIDE), dtype=torch.int32, device="cuda")
+    scratch = torch.empty((n, 65536), dtype=torch.int32, device="cuda")
+    stats = torch.empty((4, n), dtype=torch.float64, device="cuda")
+    coeff = torch.empty((3, n), dtype=torch.float64, device="cuda")
+    gpu.dev.histogram(gpu.dev.band(fr.data_ptr(), n, c, h, w), hist.data_ptr(), sp)
+    gpu.dev.ikss(hist.data_ptr(), n, stats.data_ptr(), scratch.data_ptr(), sp)
+    gpu.dev.norm_coeffs(stats.data_ptr(), n, 0, 2, coeff.data_ptr(), None, sp)
+    torch.cuda.synchronize()
+    st = stats.cpu().numpy()
+    ref = [refrun.frame_stats(host_u16(fr[f])) for f in range(n)]
+    for f in range(n):
+        assert st[0, f] == ref[f][0]
+        assert abs(st[1, f] - ref[f][1]) <= 1e-11 * ref[f][1]
+        assert st[2, f] == ref[f][2] and st[3, f] == ref[f][3]
+    cf = coeff.cpu().numpy()
+    assert cf[1, 0] == 1.0 and cf[1, 1] == ref[0][0] / ref[1][0]       # mul = L_ref / L_i (stacking.c:116-120)
