@@ -10,7 +10,11 @@ LIB_PATH = os.path.join(_HERE, "libsiril_oracle.so")
 
 NO_REJEC, PERCENTILE, SIGMA, SIGMEDIAN, WINSORIZED, LINEARFIT = range(6)
 NO_NORM, ADDITIVE, MULTIPLICATIVE, ADDITIVE_SCALING, MULTIPLICATIVE_SCALING = range(5)
-SD_GSL, SD_EXACT = 0, 1
+# sd_mode: SD_GSL = the reference's formulation of sigma (GSL's running mean / variance in x87 long double);
+# SD_EXACT = the GPU's (exact integer sums, one rounding).  FIT_EXACT is a flag OR-ed in: the straight line
+# of LINEARFIT from exact integer sums instead of gsl_fit_linear's running means.  The GPU screens with that
+# form but finishes every undecided pixel with the literal recurrences, so it is compared WITHOUT the flag.
+SD_GSL, SD_EXACT, FIT_EXACT = 0, 1, 2
 
 
 class _Args(C.Structure):

@@ -125,7 +125,7 @@ static double sd_exact(const uint16_t *d, int n) {
 }
 
 static double sd_u16(const uint16_t *d, int n, int sd_mode) {
-	return sd_mode == SO_SD_EXACT_INTEGER ? sd_exact(d, n) : sd_gsl(d, n);
+	return (sd_mode & SO_SD_EXACT_INTEGER) ? sd_exact(d, n) : sd_gsl(d, n);
 }
 
 /* gsl_fit_linear (GSL fit/linear.c) with x_i = i: intercept c0, slope c1.
@@ -145,6 +145,38 @@ static void fit_line_index(const uint16_t *y, int n, double *c0, double *c1) {
 	}
 	*c1 = m_dxdy / m_dx2;
 	*c0 = m_y - m_x * (*c1);
+}
+
+/* The same least-squares line and mean absolute residual from exact sums (SO_FIT_EXACT_SUMS; the
+ * GPU's form, csrc/ssc_fit.cuh).  With x_i = i the normal equations are integer:
+ *   slope a     = (n*Sxy - Sx*Sy) / (n*Sxx - Sx*Sx),  Sx = n(n-1)/2,  n*Sxx - Sx^2 = n^2 (n^2 - 1) / 12
+ *   intercept b = Sy/n - ((n-1)/2) * a
+ * numerator and denominator are exact integers below 2^53 (n <= 2048): ONE rounding for a, three for b,
+ * against the reference's 4n sequentially rounded running-mean updates.  The residual of sample f is
+ * y_f - fma(a, f, b); |residual| is rounded to a multiple of 2^-32 and summed as an integer, so the
+ * sum does not depend on the order (any thread layout gives the same bits);
+ * sigma = (that sum * 2^-32) / n.  Flags compare the same residual with slow*sigma and shigh*sigma
+ * (the reference divides the residual by sigma instead, stacking.c:1175,1179). */
+static void fit_exact(const uint16_t *y, int n, double *c0, double *c1, double *sigma) {
+	uint64_t Sy = 0, Sxy = 0, T = 0;
+	int i;
+	for (i = 0; i < n; i++) {
+		Sy += y[i];
+		Sxy += (uint64_t) i * y[i];
+	}
+	{
+		const int64_t num = (int64_t) ((uint64_t) n * Sxy) - (int64_t) (((uint64_t) n * (uint64_t) (n - 1) / 2) * Sy);
+		const uint64_t n2 = (uint64_t) n * (uint64_t) n;
+		const uint64_t den = n2 * (n2 - 1) / 12;
+		const double a = (double) num / (double) den;
+		*c1 = a;
+		*c0 = (double) Sy / (double) n - ((double) (n - 1) * 0.5) * a;
+	}
+	for (i = 0; i < n; i++) {
+		const double res = (double) y[i] - fma(*c1, (double) i, *c0);
+		T += (uint64_t) llrint(fabs(res) * 4294967296.0);	/* round to nearest even, as the GPU's 2^52 trick */
+	}
+	*sigma = ((double) T * (1.0 / 4294967296.0)) / (double) n;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -313,15 +345,29 @@ uint16_t so_reject_column(uint16_t *s, int N, int rejection, double sig_low, dou
 	case SO_LINEARFIT:	/* stacking.c:1750-1784 */
 		do {
 			double a, b;
+			const int exact = (sd_mode & SO_FIT_EXACT_SUMS) != 0;
+			double tl = 0.0, th = 0.0;
 			sort_u16(s, N);
-			fit_line_index(s, N, &b, &a);
-			sigma = 0.0;
-			for (f = 0; f < N; f++)
-				sigma += fabs((double) s[f] - (a * (double) f + b));
-			sigma /= (double) N;
+			if (exact) {
+				fit_exact(s, N, &b, &a, &sigma);
+				tl = sig_low * sigma;
+				th = sig_high * sigma;
+			} else {
+				fit_line_index(s, N, &b, &a);
+				sigma = 0.0;
+				for (f = 0; f < N; f++)
+					sigma += fabs((double) s[f] - (a * (double) f + b));
+				sigma /= (double) N;
+			}
 			memset(flag, 0, (size_t) N);
 			for (f = 0; f < N; f++) {
-				flag[f] = (signed char) clip_line(s[f], sig_low, sig_high, sigma, f, a, b, rej);
+				if (exact) {
+					const double res = (double) s[f] - fma(a, (double) f, b);
+					flag[f] = (signed char) (-res > tl ? -1 : (res > th ? 1 : 0));
+					if (flag[f])
+						rej[flag[f] < 0 ? 0 : 1]++;
+				} else
+					flag[f] = (signed char) clip_line(s[f], sig_low, sig_high, sigma, f, a, b, rej);
 				if (flag[f] != 0)
 					r++;
 				if (N - r <= 4) {

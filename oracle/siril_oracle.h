@@ -31,7 +31,12 @@ enum { SO_NO_NORM = 0, SO_ADDITIVE, SO_MULTIPLICATIVE, SO_ADDITIVE_SCALING, SO_M
 /* how sigma (gsl_stats_ushort_sd) is evaluated */
 enum {
 	SO_SD_GSL_LONG_DOUBLE = 0,	/* GSL's running mean/variance in x87 long double (the reference) */
-	SO_SD_EXACT_INTEGER = 1		/* sqrt(((n*Q-S*S)/(n*n)) * (n/(n-1))) from exact integer sums (the GPU) */
+	SO_SD_EXACT_INTEGER = 1,	/* sqrt(((n*Q-S*S)/(n*n)) * (n/(n-1))) from exact integer sums (the GPU) */
+	/* flag, OR-ed into sd_mode: how the straight line of LINEARFIT (gsl_fit_linear + the residual sum)
+	 * is evaluated.  Clear: GSL's running means, literally (the reference).  Set: from the exact integer
+	 * sums of y and i*y with one rounding for slope and intercept, and the mean absolute residual from
+	 * an exact fixed-point sum (order independent) -- the GPU's form, see fit_exact() */
+	SO_FIT_EXACT_SUMS = 2
 };
 
 typedef struct {

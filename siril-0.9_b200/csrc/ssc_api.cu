@@ -424,10 +424,9 @@ int run_job(const Job &job) {
 					+ it->second.scratch.cap + it->second.acc.cap;
 		}
 		// what the library itself keeps on the device besides frames and result: histograms and IKSS scratch,
-		// the linear fit's spill area (ssc_stack_mid.cu), 4 bytes per result pixel for the sigma kernel's
-		// hand-back list, and the extra source rows the y shifts reach for (source_rows())
+		// 4 bytes per result pixel for the hand-back lists of the register / warp kernels, and the extra
+		// source rows the y shifts reach for (source_rows())
 		size_t fixed = (size_t) N * (SSC_HIST_STRIDE + 65536) * 4 + (64u << 20);
-		if (job.op == OP_MEAN && job.rejection == LINEARFIT) fixed += ssc::spill_bytes_wanted();
 		int reach = 0;
 		if (job.op != OP_MEDIAN && job.seq->have_reg) {
 			int lo = 0, hi = 0;

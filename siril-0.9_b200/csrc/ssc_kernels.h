@@ -14,6 +14,7 @@ struct FitTables {
 	const double *inv;	// RN(1 / n)
 	const double *mx;	// gsl_fit_linear's running mean of x_i = i after n steps (data independent)
 	const double *mdx2;	// its running mean of (i - mx[n])^2 after n steps
+	const double *inv_den;	// RN(12 / (n^2 (n^2 - 1))): 1 / (n Sxx - Sx^2) of x_i = i (ssc_stack_warp.cu)
 	int n_max;		// 0: no tables, literal divisions
 };
 
@@ -40,8 +41,9 @@ int launch_stack_fast(const StackParams &p, int is_median, cudaStream_t stream);
 // ssc_stack_mid.cu: 65..256 frames, register network on runs of 64 + shared-memory merges
 bool mid_path_eligible(const StackParams &p, int is_median);
 int launch_stack_mid(const StackParams &p, int is_median, cudaStream_t stream);
-void release_mid_scratch(int dev);
-size_t spill_bytes_wanted();	// size of the linear fit's spill area (SSC_SPILL_BYTES overrides the 1 GB default)
+// ssc_stack_warp.cu: one warp per pixel pair -- linear fit (8..1024 frames), median of 513..1024 frames
+bool warp_path_eligible(const StackParams &p, int is_median);
+int launch_stack_warp(const StackParams &p, int is_median, cudaStream_t stream);
 // picks the register-network kernel when the shape allows it, the general kernel otherwise
 int launch_stack(const StackParams &p, int is_median, cudaStream_t stream);
 void release_kernel_scratch(int dev);	// per-device lists and tables the kernels keep between launches

@@ -150,10 +150,14 @@ int launch_stack_generic(const StackParams &p, const unsigned int *list, const u
 // FitTables (ssc_kernels.h): built once per device with the literal recurrences of gsl_fit_linear
 // for x_i = i, so that looking them up gives the very bits the per-pixel loops would compute.
 // ---------------------------------------------------------------------------
-__global__ void k_fit_tables(double *inv, double *mx, double *mdx2, int n_max) {
+__global__ void k_fit_tables(double *inv, double *mx, double *mdx2, double *inv_den, int n_max) {
 	const int n = blockIdx.x * blockDim.x + threadIdx.x;
 	if (n > n_max) return;
-	if (n == 0) { inv[0] = 0.0; mx[0] = 0.0; mdx2[0] = 0.0; return; }
+	if (n == 0) { inv[0] = 0.0; mx[0] = 0.0; mdx2[0] = 0.0; inv_den[0] = 0.0; return; }
+	{
+		const double n2 = dmul((double) n, (double) n);	// n^2 (n^2 - 1) / 12 is an integer below 2^41: exact
+		inv_den[n] = n > 1 ? ddiv(1.0, ddiv(dmul(n2, dsub(n2, 1.0)), 12.0)) : 0.0;
+	}
 	inv[n] = ddiv(1.0, (double) n);
 	double m_x = 0.0, m_dx2 = 0.0;
 	for (int i = 0; i < n; i++) m_x = dadd(m_x, ddiv(dsub((double) i, m_x), dadd((double) i, 1.0)));
@@ -165,7 +169,7 @@ __global__ void k_fit_tables(double *inv, double *mx, double *mdx2, int n_max) {
 	mdx2[n] = m_dx2;
 }
 
-static double *g_fit_store[64];	// per device: [3][SSC_GENERIC_MAX_FRAMES + 1]
+static double *g_fit_store[64];	// per device: [4][SSC_GENERIC_MAX_FRAMES + 1]
 
 static int fit_tables(FitTables &fit, cudaStream_t stream) {
 	int dev = 0;
@@ -174,16 +178,17 @@ static int fit_tables(FitTables &fit, cudaStream_t stream) {
 	const int n_max = SSC_GENERIC_MAX_FRAMES, stride = n_max + 1;
 	if (!g_fit_store[dev]) {
 		double *t = nullptr;
-		if (cudaMalloc(&t, (size_t) 3 * stride * sizeof(double)) != cudaSuccess) return SSC_ERR_CUDA;
+		if (cudaMalloc(&t, (size_t) 4 * stride * sizeof(double)) != cudaSuccess) return SSC_ERR_CUDA;
 		// built on the launching stream: ordered before the kernel that reads it; later launches on
 		// other streams of this device come after this call returned, hence the synchronisation
-		k_fit_tables<<<(stride + 127) / 128, 128, 0, stream>>>(t, t + stride, t + 2 * stride, n_max);
+		k_fit_tables<<<(stride + 127) / 128, 128, 0, stream>>>(t, t + stride, t + 2 * stride, t + 3 * stride, n_max);
 		if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { cudaFree(t); return SSC_ERR_CUDA; }
 		g_fit_store[dev] = t;
 	}
 	fit.inv = g_fit_store[dev];
 	fit.mx = g_fit_store[dev] + stride;
 	fit.mdx2 = g_fit_store[dev] + 2 * stride;
+	fit.inv_den = g_fit_store[dev] + 3 * stride;
 	fit.n_max = n_max;
 	return SSC_OK;
 }
@@ -192,7 +197,6 @@ static int fit_tables(FitTables &fit, cudaStream_t stream) {
 void release_kernel_scratch(int dev) {
 	if (dev < 0 || dev >= 64) return;
 	if (g_fit_store[dev]) { cudaFree(g_fit_store[dev]); g_fit_store[dev] = nullptr; }
-	release_mid_scratch(dev);
 	LeftoverIdStore &ids = g_leftover_id_store[dev];
 	if (ids.ids) cudaFree(ids.ids);
 	if (ids.count) cudaFree(ids.count);
@@ -215,13 +219,14 @@ static ScratchOwner g_scratch_owner[64];
 
 static int launch_stack_unchained(const StackParams &p_in, int is_median, cudaStream_t stream) {
 	StackParams p = p_in;
-	p.fit = FitTables{nullptr, nullptr, nullptr, 0};
+	p.fit = FitTables{nullptr, nullptr, nullptr, nullptr, 0};
 	if (!is_median && p.rejection == LINEARFIT) {
 		int rc = fit_tables(p.fit, stream);
 		if (rc) return rc;
 	}
-	const bool spilled_fit = !is_median && p.rejection == LINEARFIT && mid_path_eligible(p, is_median);
-	if (g_kernel_path != 1 && !spilled_fit && fast_path_eligible(p, is_median))
+	if (g_kernel_path != 1 && warp_path_eligible(p, is_median))
+		return launch_stack_warp(p, is_median, stream);
+	if (g_kernel_path != 1 && fast_path_eligible(p, is_median))
 		return launch_stack_fast(p, is_median, stream);
 	if (g_kernel_path != 1 && mid_path_eligible(p, is_median))
 		return launch_stack_mid(p, is_median, stream);

@@ -72,25 +72,11 @@ __device__ __forceinline__ void normalize_column(unsigned int *col_t, const doub
 	}
 }
 
-// The linear fit's per-pixel loops are strictly serial recurrences (gsl_fit_linear's running means) over
-// the whole column, several times per clipping iteration: with the columns in shared memory only 2-12
-// warps per SM are busy with them and every one waits on its own FP64 chain.  For that mode the sorted
-// columns are spilled to global memory instead (element-major: element i of all pixels contiguous, so a
-// warp's accesses coalesce) and k_tail_spilled runs the rejection from there with a full complement of
-// warps per SM.  The launcher walks the band in row slices so the spill area stays bounded.
-struct Spill {
-	WORD *cols;			// [n_frames][pixels] sorted columns, or nullptr: rejection straight from shared memory
-	unsigned long long *S, *Q;	// [pixels] exact sums
-	unsigned int *out_idx;		// [pixels] result element, 0xFFFFFFFF = no pixel
-	unsigned char *layer;		// [pixels]
-	unsigned int pixels;		// capacity = 2 * MID_THREADS * tiles of the launch
-};
-
 // NPAD: 128 .. 1024, the column length the merges work on (sentinels 0xFFFF behind the N samples);
 // MID_THREADS: pixel pairs per block (the block has 2 * MID_THREADS threads, see 5. above)
 template <int NPAD, int MID_THREADS>
 __global__ void __launch_bounds__(2 * MID_THREADS)
-k_stack_mid(StackParams p, unsigned int n_tiles, int is_median, Spill spill) {
+k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 	extern __shared__ unsigned int col[];			// [NPAD][MID_THREADS] packed columns
 	__shared__ double s_coef[3 * NPAD];			// offset, mul, scale
 	__shared__ int s_fast_norm;
@@ -276,17 +262,6 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median, Spill spill) {
 			const int layer = s_layer[pair];
 			Column c{reinterpret_cast<WORD *>(col) + 2 * pair + h, 2 * MID_THREADS};
 			unsigned int res;
-			if (spill.cols) {			// hand the sorted column to k_tail_spilled
-				const unsigned int px = 2 * (tile * MID_THREADS + pair) + h;
-				WORD *dst = spill.cols + px;
-				for (int i = 0; i < N; i++) dst[(size_t) i * spill.pixels] = (WORD) c.get(i);
-				spill.S[px] = s_S[tid] + s_S[2 * MID_THREADS + tid];
-				spill.Q[px] = s_Q[tid] + s_Q[2 * MID_THREADS + tid];
-				spill.out_idx[px] = active ? (oi & 0x7FFFFFFFu) + h : 0xFFFFFFFFu;
-				spill.layer[px] = (unsigned char) layer;
-				__syncthreads();
-				continue;
-			}
 			if (is_median) {			// stacking.c:765-767, double -> WORD truncation
 				res = (c.get((N - 1) >> 1) + c.get(N >> 1)) >> 1;
 			} else {
@@ -308,63 +283,11 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median, Spill spill) {
 		atomicAdd(&p.counters[tid], blk_counters[tid]);
 }
 
-// The rejection of spilled columns (see Spill): one pixel per thread, columns in global memory.
-__global__ void __launch_bounds__(128)
-k_tail_spilled(StackParams p, Spill spill, unsigned int n_px) {
-	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
-	const int tid = threadIdx.x;
-	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
-	__syncthreads();
-	const unsigned int px = blockIdx.x * blockDim.x + tid;
-	if (px < n_px) {
-		const unsigned int oi = spill.out_idx[px];
-		if (oi != 0xFFFFFFFFu) {
-			Column c{spill.cols + px, (int) spill.pixels};
-			RejectState st{0, 0, 0, 0};
-			const unsigned int res = reject_sorted_and_mean<false>(c, p.band.n_frames, p.rejection, p.sig_low, p.sig_high,
-					spill.S[px], spill.Q[px], st, nullptr, &p.fit);
-			p.out[oi] = (WORD) res;
-			const int layer = spill.layer[px];
-			if (st.rej_lo) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) st.rej_lo);
-			if (st.rej_hi) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) st.rej_hi);
-			if (st.guard) atomicAdd(&blk_counters[6], 1ull);
-			if (st.cap) atomicAdd(&blk_counters[7], 1ull);
-		}
-	}
-	__syncthreads();
-	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
-		atomicAdd(&p.counters[tid], blk_counters[tid]);
-}
-
-// spill area, per device, kept between launches (freed by release_mid_scratch)
-struct SpillStore {
-	void *mem = nullptr;
-	size_t bytes = 0;
-};
-static SpillStore g_spill_store[64];
-constexpr size_t SPILL_BYTES = (size_t) 1 << 30;	// columns of one row slice
-
-size_t spill_bytes_wanted() {
-	if (const char *e = getenv("SSC_SPILL_BYTES")) {	// tests force several slices with a small area
-		const long long v = atoll(e);
-		if (v > 0) return (size_t) v;
-	}
-	return SPILL_BYTES;
-}
-
-void release_mid_scratch(int dev) {
-	if (dev < 0 || dev >= 64) return;
-	if (g_spill_store[dev].mem) cudaFree(g_spill_store[dev].mem);
-	g_spill_store[dev] = SpillStore{};
-}
-
 // Same conditions as the 64-frame register kernel (ssc_stack_fast.cu), for 65..1024 frames.
 bool mid_path_eligible(const StackParams &p, int is_median) {
 	const ssc_band &b = p.band;
 	if (b.n_frames > 1024) return false;
-	// (up to 64 frames the register kernel is the better sorter -- except for the linear fit, whose
-	// rejection dominates and runs best from spilled columns: launch_stack sends it here)
-	if (b.n_frames <= 64 && (is_median || p.rejection != LINEARFIT || b.n_frames < 8)) return false;
+	if (b.n_frames <= 64) return false;	// the register kernel (ssc_stack_fast.cu) is the better sorter there
 	if (!is_median && (b.shiftx || b.shifty)) return false;
 	if ((b.width & 1) || (b.frame_stride & 1) || (b.layer_stride & 1)) return false;
 	if (((uintptr_t) b.frames & 3) || ((uintptr_t) p.out & 3) || (p.out_layer_stride & 1)) return false;
@@ -375,7 +298,7 @@ bool mid_path_eligible(const StackParams &p, int is_median) {
 }
 
 template <int NPAD, int MID_THREADS>
-static int launch_mid_rows(const StackParams &p, int is_median, const Spill &spill, cudaStream_t stream) {
+static int launch_mid(const StackParams &p, int is_median, cudaStream_t stream) {
 	const ssc_band &b = p.band;
 	const unsigned long long total = (unsigned long long) b.layers * b.out_rows * (b.width >> 1);
 	if (total == 0) return SSC_OK;
@@ -390,58 +313,8 @@ static int launch_mid_rows(const StackParams &p, int is_median, const Spill &spi
 		per_sm = 1;
 	unsigned long long blocks = (unsigned long long) sms * per_sm * 4;	// looping blocks, a few per resident slot
 	if (blocks > tiles) blocks = tiles;
-	k_stack_mid<NPAD, MID_THREADS><<<(unsigned int) blocks, 2 * MID_THREADS, smem, stream>>>(p, (unsigned int) tiles, is_median, spill);
+	k_stack_mid<NPAD, MID_THREADS><<<(unsigned int) blocks, 2 * MID_THREADS, smem, stream>>>(p, (unsigned int) tiles, is_median);
 	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
-}
-
-template <int NPAD, int MID_THREADS>
-static int launch_mid(const StackParams &p, int is_median, cudaStream_t stream) {
-	const ssc_band &b = p.band;
-	Spill none{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
-	if (is_median || p.rejection != LINEARFIT) return launch_mid_rows<NPAD, MID_THREADS>(p, is_median, none, stream);
-
-	// linear fit: sort a slice of rows into the spill area, reject from there, next slice
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (dev < 0 || dev >= 64) return SSC_ERR_ARG;
-	SpillStore &st = g_spill_store[dev];
-	const size_t per_px = (size_t) b.n_frames * sizeof(WORD) + 2 * sizeof(unsigned long long) + sizeof(unsigned int) + 1;
-	const size_t px_per_row = (size_t) b.layers * b.width;	// a slice takes the same rows of every layer
-	// (tiles run over layers x rows x pairs, so a slice is a range of rows of ONE launch only when it
-	// covers whole rows of all layers: slices are bands with fewer out_rows)
-	const size_t spill_bytes = spill_bytes_wanted();
-	size_t rows_per_slice = spill_bytes / (per_px * px_per_row + 1);
-	if (rows_per_slice < 1) rows_per_slice = 1;
-	if (rows_per_slice > (size_t) b.out_rows) rows_per_slice = (size_t) b.out_rows;
-	const size_t slice_pairs = (size_t) b.layers * rows_per_slice * (b.width >> 1);
-	const size_t cap_px = 2 * ((slice_pairs + MID_THREADS - 1) / MID_THREADS) * MID_THREADS;
-	const size_t need = cap_px * per_px + 64;
-	if (st.bytes < need) {
-		if (st.mem) cudaFree(st.mem);
-		st = SpillStore{};
-		if (cudaMalloc(&st.mem, need) != cudaSuccess) return SSC_ERR_CUDA;
-		st.bytes = need;
-	}
-	Spill spill;
-	char *base = (char *) st.mem;
-	spill.S = (unsigned long long *) base; base += cap_px * sizeof(unsigned long long);
-	spill.Q = (unsigned long long *) base; base += cap_px * sizeof(unsigned long long);
-	spill.out_idx = (unsigned int *) base; base += cap_px * sizeof(unsigned int);
-	spill.cols = (WORD *) base; base += cap_px * (size_t) b.n_frames * sizeof(WORD);
-	spill.layer = (unsigned char *) base;
-	spill.pixels = (unsigned int) cap_px;
-	for (int r0 = 0; r0 < b.out_rows; r0 += (int) rows_per_slice) {
-		StackParams q = p;
-		q.band.out_row0 = b.out_row0 + r0;
-		q.band.out_rows = (int) std::min<size_t>(rows_per_slice, (size_t) (b.out_rows - r0));
-		const size_t pairs = (size_t) b.layers * q.band.out_rows * (b.width >> 1);
-		const unsigned int n_px = (unsigned int) (2 * ((pairs + MID_THREADS - 1) / MID_THREADS) * MID_THREADS);
-		int rc = launch_mid_rows<NPAD, MID_THREADS>(q, 0, spill, stream);
-		if (rc) return rc;
-		k_tail_spilled<<<(n_px + 127) / 128, 128, 0, stream>>>(q, spill, n_px);
-		if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
-	}
-	return SSC_OK;
 }
 
 // columns of 64 KB per block: 64 pixel pairs up to 256 frames, 32 up to 512, 16 up to 1024

@@ -1,0 +1,428 @@
+// ssc_stack_warp.cu -- K2/K3, one WARP per pixel pair: linear-fit clipping for 8..1024 frames
+// (BASELINE.json's cfg5: 1000 frames) and the median of 513..1024 frames, without registration shifts.
+//
+// The linear fit (stacking.c:1750-1784) is the one rejection whose cost per iteration is proportional
+// to the whole column: a least-squares line through the SORTED samples, the mean absolute residual,
+// one flag per sample.  The reference (gsl_fit_linear) evaluates it as 4 N strictly sequential
+// running-mean updates; one thread per pixel doing the same waits on a single FP64 dependency chain
+// (408 ms for cfg5 in round 1's form).  Here a warp owns the column:
+//   1. the block stages a tile of 8 pixel pairs x N frames in shared memory with 4-byte cp.async
+//      (16 consecutive pixels of a row: whole 32-byte sectors), each warp reads its pair's column
+//      conflict-free, lane l taking frames l, l+32, ... and normalizing them (exact FP64);
+//   2. the column is sorted in registers as packed u16x2 (both pixels at once): a Batcher network on
+//      each lane's R samples, then bitonic merges across lanes with shuffles (first stage against the
+//      reversed partner, so every run stays ascending) -- lane l ends up with sorted samples
+//      [l R, (l+1) R);
+//   3. per pixel, every clipping iteration is two passes over the lane's R samples plus a few warp
+//      reductions: the line comes from EXACT integer sums (sum y, sum i y: slope and intercept carry
+//      one rounding instead of 4 N), the residuals are summed in FP64, and each sample is compared
+//      with the two thresholds widened and narrowed by a safety margin.  If every comparison is decided
+//      outside the margin -- which covers the rounding of both formulations by three orders of
+//      magnitude -- the flags are the ones the reference's arithmetic produces, and the result is
+//      bit-identical to it (oracle/siril_oracle.c restates both forms; tests/test_oracle_kat.py).
+//      A pixel with a comparison inside the margin (an exact tie, a vanishing sigma) is handed back by
+//      index and finished by the general kernel with gsl_fit_linear's literal recurrences
+//      (ssc_column.cuh), so no result ever depends on the screening arithmetic;
+//   4. the reference's `if (N - r <= 4) break;` (stacking.c:1771) is applied from prefix counts of the
+//      flags: the samples behind the break keep flag 0, the event is counted (guard_fired).
+#include "ssc_column.cuh"
+#include "ssc_kernels.h"
+#include "ssc_leftover.cuh"
+#include "ssc_network.cuh"
+
+namespace ssc {
+
+constexpr int WARP_PAIRS = 8;		// warps per block = pixel pairs per tile
+constexpr int WARP_PITCH = 9;		// words per frame in the staging tile: odd, so a warp's column read is conflict-free
+constexpr unsigned int FULL = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// sorting: R packed samples per lane, 32 R per warp
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void lane_sort(unsigned int (&v)[R]) {
+	if constexpr (R == 32 || R == 16) {
+		sort_network<R>(v);
+	} else {
+#pragma unroll
+		for (int k = 2; k <= R; k <<= 1)
+#pragma unroll
+			for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+				for (int i = 0; i < R; i++) {
+					const int l = i ^ j;
+					if (l > i) {
+						const unsigned int lo = __vminu2(v[i], v[l]), hi = __vmaxu2(v[i], v[l]);
+						if ((i & k) == 0) { v[i] = lo; v[l] = hi; } else { v[i] = hi; v[l] = lo; }
+					}
+				}
+	}
+}
+
+template <int R>
+__device__ __forceinline__ void warp_sort(unsigned int (&v)[R], const int lane) {
+	lane_sort<R>(v);
+#pragma unroll
+	for (int m = 1; m <= 16; m <<= 1) {	// runs of m lanes -> runs of 2 m lanes
+		{	// element k of the lower run against element 2 m R - 1 - k of the upper run
+			unsigned int q[R];
+#pragma unroll
+			for (int r = 0; r < R; r++) q[r] = __shfl_xor_sync(FULL, v[R - 1 - r], 2 * m - 1);
+			const bool upper = (lane & m) != 0;
+#pragma unroll
+			for (int r = 0; r < R; r++) v[r] = upper ? __vmaxu2(v[r], q[r]) : __vminu2(v[r], q[r]);
+		}
+#pragma unroll
+		for (int d = m >> 1; d >= 1; d >>= 1) {	// half-cleaners between lanes
+			const bool upper = (lane & d) != 0;
+#pragma unroll
+			for (int r = 0; r < R; r++) {
+				const unsigned int q = __shfl_xor_sync(FULL, v[r], d);
+				v[r] = upper ? __vmaxu2(v[r], q) : __vminu2(v[r], q);
+			}
+		}
+#pragma unroll
+		for (int d = R >> 1; d >= 1; d >>= 1)	// half-cleaners inside the lane
+#pragma unroll
+			for (int i = 0; i < R; i++)
+				if ((i & d) == 0) {
+					const unsigned int lo = __vminu2(v[i], v[i + d]);
+					v[i + d] = __vmaxu2(v[i], v[i + d]);
+					v[i] = lo;
+				}
+	}
+}
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+	for (int o = 16; o >= 1; o >>= 1) x = dadd(x, __shfl_xor_sync(FULL, x, o));	// a + b == b + a: every lane gets the same bits
+	return x;
+}
+
+__device__ __forceinline__ int warp_sum(int x) {
+	return (int) __reduce_add_sync(FULL, (unsigned int) x);
+}
+
+// inclusive prefix sum over the lanes
+__device__ __forceinline__ int warp_scan(int x, const int lane) {
+#pragma unroll
+	for (int o = 1; o <= 16; o <<= 1) {
+		const int t = __shfl_up_sync(FULL, x, o);
+		if (lane >= o) x += t;
+	}
+	return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// linear-fit clipping of one pixel (half `sel` of the packed column).  false: hand the pixel back.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ bool fit_pixel(const unsigned int (&v)[R], const int sel, const int N, const int lane,
+		const double slow, const double shigh, const FitTables &fit, double *__restrict__ y, unsigned int &result,
+		unsigned int &rej_lo, unsigned int &rej_hi, int &guard, int &cap) {
+	// y: this lane's R samples as doubles, in the warp's own piece of shared memory (y[r * 32]: conflict-free;
+	// in registers they would cost 2 R of them next to the packed column)
+	unsigned int alive = 0, Sy = 0, Wl = 0;	// Sy = sum of my live samples, Wl = sum of (rank inside the lane) * sample
+	int cnt = 0;
+#pragma unroll
+	for (int r = 0; r < R; r++) {
+		const unsigned int yi = sel ? v[r] >> 16 : v[r] & 0xFFFFu;
+		y[r * 32] = word_to_double(yi);
+		if (lane * R + r < N) {
+			alive |= 1u << r;
+			Wl += (unsigned int) cnt * yi;
+			Sy += yi;
+			cnt++;
+		}
+	}
+	int n_cur = N, r_cum = 0, iter = 0;
+	rej_lo = rej_hi = 0;
+	for (;;) {
+		const int base = warp_scan(cnt, lane) - cnt;	// index of my first live sample in the sorted survivors
+		// sum y and sum i y of the survivors: exact integers below 2^53, in doubles
+		const double sy = warp_sum((double) Sy);
+		const double sxy = warp_sum(__fma_rn((double) base, (double) Sy, (double) Wl));
+		const double n = (double) n_cur;
+		// slope = (n Sxy - Sx Sy) / (n Sxx - Sx^2), Sx = n (n-1) / 2; numerator exact, one rounding for the quotient
+		const double num = dsub(dmul(n, sxy), dmul(dmul(dmul(n, dsub(n, 1.0)), 0.5), sy));
+		const double a = dmul(num, fit.inv_den[n_cur]);
+		const double b = dsub(dmul(sy, fit.inv[n_cur]), dmul(dmul(dsub(n, 1.0), 0.5), a));
+		const double pred0 = __fma_rn(a, (double) base, b);
+		double pred = pred0, t = 0.0;
+#pragma unroll 8
+		for (int r = 0; r < R; r++)
+			if (alive & (1u << r)) {
+				t = dadd(t, fabs(dsub(y[r * 32], pred)));
+				pred = dadd(pred, a);
+			}
+		const double sigma = dmul(warp_sum(t), fit.inv[n_cur]);
+		if (!(sigma > 0.05)) return false;	// (nearly) perfect line: the reference divides by this sigma
+		const double tl = dmul(slow, sigma), th = dmul(shigh, sigma);
+		const double ml = dadd(dmul(fabs(tl), 1e-7), 1e-6), mh = dadd(dmul(fabs(th), 1e-7), 1e-6);
+		const double tl_s = dadd(tl, ml), tl_m = dsub(tl, ml), th_s = dadd(th, mh), th_m = dsub(th, mh);
+		unsigned int fm = 0, lom = 0;
+		bool near = false;
+		pred = pred0;
+#pragma unroll 8
+		for (int r = 0; r < R; r++)
+			if (alive & (1u << r)) {
+				const double res = dsub(y[r * 32], pred);
+				pred = dadd(pred, a);
+				const bool lo_s = -res > tl_s, lo_m = -res > tl_m, hi_s = res > th_s, hi_m = res > th_m;
+				near |= (lo_s != lo_m) | (!lo_s & (hi_s != hi_m));
+				if (lo_s) { lom |= 1u << r; fm |= 1u << r; }	// line_clipping tests the low side first (:1175)
+				else if (hi_s) fm |= 1u << r;
+			}
+		if (__any_sync(FULL, near)) return false;
+		// the reference's scan: r++ per flagged sample, `if (N - r <= 4) break;` after every sample
+		const int c = __popc(fm);
+		const int e = warp_scan(c, lane) - c;
+		const int flagged = __shfl_sync(FULL, e + c, 31);
+		const int need = n_cur - 4 - r_cum;	// the break follows the need-th flagged sample of this pass
+		if (need <= 0) {			// already true: only the very first sample is looked at
+			fm = (base == 0 && cnt > 0) ? fm & (alive & (0u - alive)) : 0u;
+			if (n_cur > 1) guard = 1;
+		} else if (flagged >= need) {
+			int hit = 0;
+			if (e < need && need <= e + c) {	// the need-th flagged sample is mine: where does it sit?
+				unsigned int tt = fm;
+				for (int k = 1; k < need - e; k++) tt &= tt - 1;
+				const unsigned int bit = tt & (0u - tt);
+				hit = base + __popc(alive & (bit - 1)) < n_cur - 1;
+			}
+			if (__any_sync(FULL, hit)) guard = 1;
+			int keep = need - e;
+			keep = keep < 0 ? 0 : (keep > c ? c : keep);
+			unsigned int tt = fm, kept = 0;
+			for (int k = 0; k < keep; k++) { kept |= tt & (0u - tt); tt &= tt - 1; }
+			fm = kept;
+		}
+		lom &= fm;
+		const int removed = warp_sum(__popc(fm));
+		rej_lo += __popc(lom);
+		rej_hi += __popc(fm & ~lom);
+		r_cum += removed;
+		if (fm) {	// my survivors changed: their sums again
+			alive &= ~fm;
+			Sy = 0; Wl = 0; cnt = 0;
+#pragma unroll
+			for (int r = 0; r < R; r++)
+				if (alive & (1u << r)) {
+					const unsigned int yi = sel ? v[r] >> 16 : v[r] & 0xFFFFu;
+					Wl += (unsigned int) cnt * yi;
+					Sy += yi;
+					cnt++;
+				}
+		}
+		n_cur -= removed;
+		if (++iter >= SSC_ITER_CAP) { cap = 1; break; }
+		if (!(removed > 0 && n_cur > 3)) break;
+	}
+	rej_lo = (unsigned int) warp_sum((int) rej_lo);
+	rej_hi = (unsigned int) warp_sum((int) rej_hi);
+	result = mean_to_word<false>((unsigned long long) (unsigned int) warp_sum((int) Sy), n_cur);	// stacking.c:1790-1794
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(32 * WARP_PAIRS, 2)
+k_stack_warp(StackParams p, unsigned int n_tiles, unsigned int tiles_per_row, int is_median, LeftoverList list) {
+	constexpr int NPAD = 32 * R;
+	extern __shared__ __align__(16) unsigned int stage[];	// [NPAD][WARP_PITCH] raw packed pairs, double y[warps][R][32], double coef[3][NPAD]
+	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
+	__shared__ int s_fast_norm;
+	const ssc_band &b = p.band;
+	const int W = b.width, W2 = W >> 1, N = b.n_frames, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
+	double *s_y = reinterpret_cast<double *>(stage + NPAD * WARP_PITCH) + warp * NPAD + lane;
+	double *s_coef = reinterpret_cast<double *>(stage + NPAD * WARP_PITCH) + (is_median ? 0 : WARP_PAIRS * NPAD);
+
+	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
+	if (tid == 0) s_fast_norm = 1;
+	__syncthreads();
+	if (norm) {
+		for (int f = tid; f < NPAD; f += blockDim.x) {
+			const bool have = f < N;
+			const double off = have ? p.coeff[f] : 0.0, mul = have ? p.coeff[N + f] : 1.0, sc = have ? p.coeff[2 * N + f] : 1.0;
+			s_coef[f] = off;
+			s_coef[NPAD + f] = mul;
+			s_coef[2 * NPAD + f] = sc;
+			if (have) {	// domain of the 2^52 tricks (ssc_network.cuh): every intermediate stays below 2^31
+				const bool additive = p.normalize == ADDITIVE || p.normalize == ADDITIVE_SCALING;
+				const double bound = additive ? dadd(dmul(fabs(sc), 65535.0), fabs(off)) : dmul(dmul(fabs(sc), 65535.0), fabs(mul));
+				if (!(bound < 2147483000.0)) s_fast_norm = 0;
+			}
+		}
+	}
+	__syncthreads();
+	const bool fast_norm = s_fast_norm != 0;
+	const unsigned int sbase = (unsigned int) __cvta_generic_to_shared(stage);
+	const unsigned long long fstride = (unsigned long long) b.frame_stride * sizeof(WORD);
+
+	for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const unsigned int row = tile / tiles_per_row;
+		const int x2_0 = (int) (tile - row * tiles_per_row) * WARP_PAIRS;
+		const int layer = (int) (row / (unsigned int) b.out_rows);
+		const int rr = (int) (row - (unsigned int) layer * (unsigned int) b.out_rows);
+		const int Rr = b.out_row0 + rr;				// result storage row (stacking.c:731,1600)
+		const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - Rr : Rr;
+		const size_t row_words = ((size_t) layer * b.layer_stride + (size_t) (srow - b.buf_row0) * W) >> 1;
+
+		// ---- 1. stage the tile: thread -> (pair tid % 8, frames tid / 8, tid / 8 + 32, ...) ----
+		{
+			const int j = tid & (WARP_PAIRS - 1);
+			int x2 = x2_0 + j;
+			if (x2 >= W2) x2 = W2 - 1;			// ragged row end: a duplicate, never written back
+			const char *src = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames) + row_words + x2);
+			for (int f = tid >> 3; f < N; f += 32)
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::
+						"r"(sbase + (unsigned int) ((f * WARP_PITCH + j) * (int) sizeof(unsigned int))),
+						"l"(src + (unsigned long long) f * fstride) : "memory");
+			asm volatile("cp.async.commit_group;" ::: "memory");
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+		}
+		__syncthreads();
+
+		// ---- normalization in place (stacking.c:1635-1652, :750-764), a rolled loop over the tile ----
+		if (norm) {
+			for (int idx = tid; idx < N * WARP_PAIRS; idx += 32 * WARP_PAIRS) {
+				const int f = idx >> 3;
+				unsigned int *slot = stage + f * WARP_PITCH + (idx & (WARP_PAIRS - 1));
+				unsigned int w = *slot;
+				const double off = s_coef[f], mul = s_coef[NPAD + f], sc = s_coef[2 * NPAD + f];
+				unsigned long long qa = 0, qb = 0;
+				if (!fast_norm) {
+					w = normalize_sample(w & 0xFFFFu, p.normalize, off, mul, sc)
+							| (normalize_sample(w >> 16, p.normalize, off, mul, sc) << 16);
+				} else {
+					switch (p.normalize) {
+					case ADDITIVE: w = normalize_pair_fast<ADDITIVE>(w, off, mul, sc, qa, qb); break;
+					case MULTIPLICATIVE: w = normalize_pair_fast<MULTIPLICATIVE>(w, off, mul, sc, qa, qb); break;
+					case ADDITIVE_SCALING: w = normalize_pair_fast<ADDITIVE_SCALING>(w, off, mul, sc, qa, qb); break;
+					default: w = normalize_pair_fast<MULTIPLICATIVE_SCALING>(w, off, mul, sc, qa, qb); break;
+					}
+				}
+				*slot = w;
+			}
+			__syncthreads();
+		}
+		// ---- my pair's column: lane l takes frames l, l + 32, ... (sentinels sort behind the samples) ----
+		unsigned int v[R];
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			const int f = r * 32 + lane;
+			v[r] = f < N ? stage[f * WARP_PITCH + warp] : 0xFFFFFFFFu;
+		}
+		__syncthreads();					// the staging tile may be overwritten now
+
+		// ---- 2. sort: lane l ends up with sorted samples [l R, (l + 1) R) of both pixels ----
+		warp_sort<R>(v, lane);
+
+		const int x2 = x2_0 + warp;
+		const bool active = x2 < W2;				// warp-uniform
+		const size_t out_idx = (size_t) layer * p.out_layer_stride + (size_t) (Rr - p.out_buf_row0) * W + 2 * (size_t) x2;
+		if (is_median) {					// stacking.c:765-767, double -> WORD truncation
+			const int m1 = (N - 1) >> 1, m2 = N >> 1;
+			unsigned int a = 0, c = 0;
+#pragma unroll
+			for (int r = 0; r < R; r++) {
+				if (r == (m1 & (R - 1))) a = v[r];
+				if (r == (m2 & (R - 1))) c = v[r];
+			}
+			a = __shfl_sync(FULL, a, m1 / R);
+			c = __shfl_sync(FULL, c, m2 / R);
+			if (active && lane == 0) {
+				const unsigned int lo = ((a & 0xFFFFu) + (c & 0xFFFFu)) >> 1, hi = ((a >> 16) + (c >> 16)) >> 1;
+				*reinterpret_cast<unsigned int *>(p.out + out_idx) = lo | (hi << 16);
+			}
+			continue;
+		}
+		// ---- 3. linear-fit clipping, one pixel of the pair after the other ----
+		if (active) {
+#pragma unroll 1
+			for (int sel = 0; sel < 2; sel++) {
+				unsigned int res = 0, rej_lo = 0, rej_hi = 0;
+				int guard = 0, cap = 0;
+				const bool done = fit_pixel<R>(v, sel, N, lane, p.sig_low, p.sig_high, p.fit, s_y, res, rej_lo, rej_hi, guard, cap);
+				if (lane == 0) {
+					if (done) {
+						p.out[out_idx + sel] = (WORD) res;
+						if (rej_lo) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) rej_lo);
+						if (rej_hi) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) rej_hi);
+						if (guard) atomicAdd(&blk_counters[6], 1ull);
+						if (cap) atomicAdd(&blk_counters[7], 1ull);
+					} else {
+						const unsigned int slot = atomicAdd(list.count, 1u);
+						if (slot < list.capacity)
+							list.ids[slot] = (unsigned int) (((size_t) layer * b.out_rows + rr) * W + 2 * x2 + sel);
+					}
+				}
+			}
+		}
+	}
+	__syncthreads();
+	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
+		atomicAdd(&p.counters[tid], blk_counters[tid]);
+}
+
+// Same shape conditions as the other packed-pair kernels; linear fit from 8 frames on (fewer: the
+// general kernel), the median above 512 frames (below, ssc_stack_fast.cu / ssc_stack_mid.cu are the
+// better sorters).
+bool warp_path_eligible(const StackParams &p, int is_median) {
+	const ssc_band &b = p.band;
+	if (b.n_frames > 1024) return false;
+	if (is_median ? b.n_frames <= 512 : (p.rejection != LINEARFIT || b.n_frames < 8)) return false;
+	if (!is_median && (b.shiftx || b.shifty)) return false;
+	if ((b.width & 1) || (b.frame_stride & 1) || (b.layer_stride & 1)) return false;
+	if (((uintptr_t) b.frames & 3) || ((uintptr_t) p.out & 3) || (p.out_layer_stride & 1)) return false;
+	if ((unsigned long long) b.layers * b.out_rows * b.width >= 0xFFFFFFF0ull) return false;	// 32-bit pixel ids
+	return true;
+}
+
+template <int R>
+static int launch_warp(const StackParams &p, int is_median, cudaStream_t stream) {
+	const ssc_band &b = p.band;
+	constexpr int NPAD = 32 * R;
+	const unsigned long long tiles_per_row = ((unsigned long long) (b.width >> 1) + WARP_PAIRS - 1) / WARP_PAIRS;
+	const unsigned long long tiles = tiles_per_row * b.layers * b.out_rows;
+	if (tiles == 0) return SSC_OK;
+	if (tiles >= 0xFFFFFFF0ull) return SSC_ERR_ARG;
+	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
+	const size_t smem = (size_t) NPAD * WARP_PITCH * sizeof(unsigned int) + (norm ? (size_t) 3 * NPAD * sizeof(double) : 0)
+			+ (is_median ? 0 : (size_t) WARP_PAIRS * NPAD * sizeof(double));
+	if (cudaFuncSetAttribute(k_stack_warp<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
+		return SSC_ERR_CUDA;
+	LeftoverList list{nullptr, 0, nullptr};
+	const unsigned long long pixels = (unsigned long long) b.layers * b.out_rows * b.width;
+	if (!is_median) {
+		int rc = leftover_ids(pixels, list, stream);
+		if (rc) return rc;
+	}
+	int dev = 0, sms = 148, per_sm = 1;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stack_warp<R>, 32 * WARP_PAIRS, smem) != cudaSuccess || per_sm < 1)
+		per_sm = 1;
+	unsigned long long blocks = (unsigned long long) sms * per_sm * 4;	// looping blocks, a few per resident slot
+	if (blocks > tiles) blocks = tiles;
+	k_stack_warp<R><<<(unsigned int) blocks, 32 * WARP_PAIRS, smem, stream>>>(p, (unsigned int) tiles, (unsigned int) tiles_per_row, is_median, list);
+	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
+	if (!is_median)	// pixels the screening could not decide: gsl_fit_linear's literal recurrences (ssc_column.cuh)
+		return launch_stack_generic(p, list.ids, list.count, (unsigned int) pixels, 0, stream);
+	return SSC_OK;
+}
+
+int launch_stack_warp(const StackParams &p, int is_median, cudaStream_t stream) {
+	const int n = p.band.n_frames;
+	if (n <= 32) return launch_warp<1>(p, is_median, stream);
+	if (n <= 64) return launch_warp<2>(p, is_median, stream);
+	if (n <= 128) return launch_warp<4>(p, is_median, stream);
+	if (n <= 256) return launch_warp<8>(p, is_median, stream);
+	if (n <= 512) return launch_warp<16>(p, is_median, stream);
+	return launch_warp<32>(p, is_median, stream);
+}
+
+}  // namespace ssc

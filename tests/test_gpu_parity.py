@@ -347,18 +347,41 @@ def test_mid_kernel_equals_general_kernel(gpu, port, rej, n, norm):
         assert a.guard_fired == same["guard_fired"]
 
 
-def test_mid_kernel_linear_fit_in_row_slices(gpu, port, monkeypatch):
-    """Linear fit on 65..1024 frames spills the sorted columns to global memory and walks the band in row
-    slices (ssc_stack_mid.cu); a tiny spill area forces many slices, RGB and an odd slice remainder."""
-    fr = synth.make_frames(72, 3, 11, 40, seed=12, outlier_p=8e-3, zero_p=2e-3, stars=2)
-    monkeypatch.setenv("SSC_SPILL_BYTES", str(3 * 40 * 3 * (72 * 2 + 21)))          # three rows per slice
-    res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), 5, (5.0, 2.5), 3)
-    monkeypatch.delenv("SSC_SPILL_BYTES")
-    one = gpu.stack_mean_with_rejection(gpu.Sequence(fr), 5, (5.0, 2.5), 3)            # one slice
-    same = port.stack_mean(fr, 5, (5.0, 2.5), 3, coeff=res.coeff, sd_mode=port.SD_EXACT)
-    for r in (res, one):
-        assert np.array_equal(r.data, same["out"]) and np.array_equal(r.irej, same["irej"])
-        assert r.guard_fired == same["guard_fired"]
+@pytest.mark.parametrize("n", [8, 12, 31, 32, 33, 64, 100, 200, 257, 513, 1000])
+def test_warp_kernel_linear_fit(gpu, port, n):
+    """ssc_stack_warp.cu: one warp per pixel pair, every lane-count instantiation, RGB, SER order, a row
+    width that leaves the last tile ragged; and columns the exact-sums screening cannot decide -- constant
+    columns (sigma = 0), perfect arithmetic progressions, an exact rational tie at the high threshold --
+    which must come back from the literal path with the reference's result."""
+    w = 44 if n <= 257 else 20
+    fr = synth.make_frames(n, 3, 5, w, seed=3 * n, outlier_p=8e-3, zero_p=2e-3, stars=1)
+    fr[:, 0, 0, 0:6] = 65535                                             # saturated: sigma 0
+    fr[:, 1, 1, 3] = 0
+    fr[:, 2, 2, 5] = (np.arange(n) * (60000 // n)).astype(np.uint16)     # a perfect line: residuals ~ 0
+    fr[:, 2, 2, 6] = 1000 + (np.arange(n) % 2)                           # two-valued
+    if n == 12:                                                          # residual / sigma == 2.5 exactly in iteration 3
+        fr[:, 0, 3, 7] = [1058, 1142, 1205, 1252, 1350, 1357, 1359, 1366, 1464, 1467, 1502, 1565]
+    for ro in (0, 1):
+        for norm in (0, 3):
+            res = gpu.stack_mean_with_rejection(gpu.Sequence(fr, row_order=ro), 5, (5.0, 2.5), norm)
+            same = port.stack_mean(fr, 5, (5.0, 2.5), norm, coeff=res.coeff, row_order=ro, sd_mode=port.SD_EXACT)
+            assert np.array_equal(res.data, same["out"]), (ro, norm)
+            assert np.array_equal(res.irej, same["irej"]) and res.guard_fired == same["guard_fired"]
+    res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), 5, (-1.0, -1.0), 0)   # everything is flagged: the guard
+    same = port.stack_mean(fr, 5, (-1.0, -1.0), 0, sd_mode=port.SD_EXACT)
+    assert np.array_equal(res.data, same["out"]) and np.array_equal(res.irej, same["irej"])
+    assert res.guard_fired == same["guard_fired"] > 0
+
+
+@pytest.mark.parametrize("n", [513, 777, 1024])
+def test_warp_kernel_median(gpu, port, n):
+    fr = synth.make_random(n, 3, 4, 36, seed=n)
+    for ro in (0, 1):
+        res = gpu.stack_median(gpu.Sequence(fr, row_order=ro))
+        assert np.array_equal(res.data, port.stack_median(fr, row_order=ro)["out"])
+    fr = synth.make_frames(n, 1, 4, 36, seed=n, stars=1)
+    res = gpu.stack_median(gpu.Sequence(fr), normalize=4, want_coeff=True)
+    assert np.array_equal(res.data, port.stack_median(fr, normalize=4, coeff=res.coeff)["out"])
 
 
 def test_mid_kernel_rgb_ser_and_fallbacks(gpu, port):

@@ -3,6 +3,8 @@ the reference has no tests of its own, so these fix the quirks in writing."""
 import numpy as np
 import pytest
 
+import synth
+
 
 def col(port, values, rej, sig, sd_mode=0):
     return port.reject_column(values, rej, sig, sd_mode)
@@ -108,3 +110,21 @@ def test_ikss_on_constant_and_empty(port):
     hist[1234] = 500
     loc, sc, it = port.ikss_hist(hist)
     assert abs(loc - 1234.0) < 1e-9 and sc == 0.0              # mad = 0 -> bwmv = 0 -> scale 0
+
+
+def test_fit_formulations_agree(port):
+    """LINEARFIT: the straight line from exact integer sums (what the warp kernel screens with,
+    SO_FIT_EXACT_SUMS) against gsl_fit_linear's literal running means.  Away from exact ties of a
+    residual with a threshold both flag the same samples: identical images and counters on seeded
+    stacks; the one known tie (residual / sigma == 2.5 exactly in the third iteration) is the kind of
+    pixel the kernel hands back to the literal path."""
+    for n, seed in ((24, 1), (64, 2), (200, 3), (1000, 4)):
+        fr = synth.make_frames(n, 1, 12, 96, seed=seed, outlier_p=5e-3, zero_p=1e-3, stars=3, planetary=(n == 1000))
+        lit = port.stack_mean(fr, port.LINEARFIT, (5.0, 2.5), sd_mode=port.SD_EXACT)
+        exa = port.stack_mean(fr, port.LINEARFIT, (5.0, 2.5), sd_mode=port.SD_EXACT | port.FIT_EXACT)
+        assert np.array_equal(lit["out"], exa["out"]), n
+        assert np.array_equal(lit["irej"], exa["irej"]) and lit["guard_fired"] == exa["guard_fired"]
+    tie = [1058, 1142, 1205, 1252, 1350, 1357, 1359, 1366, 1464, 1467, 1502, 1565]
+    a = port.reject_column(tie, port.LINEARFIT, (5.0, 2.5), port.SD_EXACT)
+    b = port.reject_column(tie, port.LINEARFIT, (5.0, 2.5), port.SD_EXACT | port.FIT_EXACT)
+    assert a[0] != b[0]                                      # rounding noise decides an exact tie
