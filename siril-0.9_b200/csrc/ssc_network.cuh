@@ -27,6 +27,21 @@ __device__ __forceinline__ void sort_network(unsigned int (&v)[NP]) {
 #undef SSC_CE
 }
 
+// The same network with every comparator half removed that cannot reach the ranks the register sigma
+// clipping reads (ssc_stack_fast.cu MODE_SIGMA_REG: 0..2, NP/2-3..NP/2+1, NP-6..NP-1): 888 instead of
+// 1086 packed min/max operations for 64 frames.  Only those ranks are valid afterwards.
+template <int NP>
+__device__ __forceinline__ void sort_network_sigma_ranks(unsigned int (&v)[NP]) {
+#define SSC_CE(a, b) { unsigned int lo_ = __vminu2(v[a], v[b]); v[b] = __vmaxu2(v[a], v[b]); v[a] = lo_; }
+#define SSC_MIN(a, b) { v[a] = __vminu2(v[a], v[b]); }
+#define SSC_MAX(a, b) { v[b] = __vmaxu2(v[a], v[b]); }
+	if constexpr (NP == 32) { SSC_SORTNET_32_SIGMA }
+	else { SSC_SORTNET_64_SIGMA }
+#undef SSC_CE
+#undef SSC_MIN
+#undef SSC_MAX
+}
+
 // One sample pair through normalization (stacking.c:1635-1652), KIND = the reference's enum value.
 // ADDITIVE / MULTIPLICATIVE have scale == 1.0 exactly (stacking.c:130-134), and x * 1.0 == x.
 template <int KIND>

@@ -438,7 +438,7 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 			// candidate window (a third low, a sixth high) goes to the leftover list.  With NP >= 32
 			// and at most 7 rejections the reference's "N - r <= 4" break (:1684) cannot be reached.
 			static_assert(FULL && NP >= 32 && (NP & (NP - 1)) == 0, "needs a full stack of 32 or 64 frames");
-			sort_network<NP>(v);
+			sort_network_sigma_ranks<NP>(v);	// only the ranks read below are in place (the hand-back kernel sorts fully)
 			bool need[2];
 #pragma unroll
 			for (int h = 0; h < 2; h++) {

@@ -103,6 +103,11 @@ __device__ __forceinline__ int warp_sum(int x) {
 	return (int) __reduce_add_sync(FULL, (unsigned int) x);
 }
 
+// acc += x where cond != 0: a predicated add, never a branch (the per-sample loops below are straight-line code)
+__device__ __forceinline__ void add_if(double &acc, const double x, const unsigned int cond) {
+	asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(x), "r"(cond));
+}
+
 // inclusive prefix sum over the lanes
 __device__ __forceinline__ int warp_scan(int x, const int lane) {
 #pragma unroll
@@ -150,30 +155,29 @@ __device__ __forceinline__ bool fit_pixel(const unsigned int (&v)[R], const int 
 		const double pred0 = __fma_rn(a, (double) base, b);
 		double pred = pred0, t = 0.0;
 #pragma unroll 8
-		for (int r = 0; r < R; r++)
-			if (alive & (1u << r)) {
-				t = dadd(t, fabs(dsub(y[r * 32], pred)));
-				pred = dadd(pred, a);
-			}
+		for (int r = 0; r < R; r++) {
+			const unsigned int on = alive & (1u << r);
+			add_if(t, fabs(dsub(y[r * 32], pred)), on);
+			add_if(pred, a, on);
+		}
 		const double sigma = dmul(warp_sum(t), fit.inv[n_cur]);
 		if (!(sigma > 0.05)) return false;	// (nearly) perfect line: the reference divides by this sigma
 		const double tl = dmul(slow, sigma), th = dmul(shigh, sigma);
 		const double ml = dadd(dmul(fabs(tl), 1e-7), 1e-6), mh = dadd(dmul(fabs(th), 1e-7), 1e-6);
 		const double tl_s = dadd(tl, ml), tl_m = dsub(tl, ml), th_s = dadd(th, mh), th_m = dsub(th, mh);
-		unsigned int fm = 0, lom = 0;
-		bool near = false;
+		unsigned int fm = 0, lom = 0, near = 0;
 		pred = pred0;
 #pragma unroll 8
-		for (int r = 0; r < R; r++)
-			if (alive & (1u << r)) {
-				const double res = dsub(y[r * 32], pred);
-				pred = dadd(pred, a);
-				const bool lo_s = -res > tl_s, lo_m = -res > tl_m, hi_s = res > th_s, hi_m = res > th_m;
-				near |= (lo_s != lo_m) | (!lo_s & (hi_s != hi_m));
-				if (lo_s) { lom |= 1u << r; fm |= 1u << r; }	// line_clipping tests the low side first (:1175)
-				else if (hi_s) fm |= 1u << r;
-			}
-		if (__any_sync(FULL, near)) return false;
+		for (int r = 0; r < R; r++) {
+			const unsigned int on = alive & (1u << r);
+			const double res = dsub(y[r * 32], pred);
+			add_if(pred, a, on);
+			const bool lo_s = -res > tl_s, lo_m = -res > tl_m, hi_s = res > th_s, hi_m = res > th_m;
+			near |= ((lo_s != lo_m) | (!lo_s & (hi_s != hi_m))) ? on : 0u;
+			lom |= lo_s ? on : 0u;				// line_clipping tests the low side first (:1175)
+			fm |= (lo_s | hi_s) ? on : 0u;
+		}
+		if (__any_sync(FULL, near != 0)) return false;
 		// the reference's scan: r++ per flagged sample, `if (N - r <= 4) break;` after every sample
 		const int c = __popc(fm);
 		const int e = warp_scan(c, lane) - c;
@@ -206,13 +210,13 @@ __device__ __forceinline__ bool fit_pixel(const unsigned int (&v)[R], const int 
 			alive &= ~fm;
 			Sy = 0; Wl = 0; cnt = 0;
 #pragma unroll
-			for (int r = 0; r < R; r++)
-				if (alive & (1u << r)) {
-					const unsigned int yi = sel ? v[r] >> 16 : v[r] & 0xFFFFu;
-					Wl += (unsigned int) cnt * yi;
-					Sy += yi;
-					cnt++;
-				}
+			for (int r = 0; r < R; r++) {
+				const unsigned int on = (alive >> r) & 1u;
+				const unsigned int yi = (sel ? v[r] >> 16 : v[r] & 0xFFFFu) * on;
+				Wl += (unsigned int) cnt * yi;
+				Sy += yi;
+				cnt += (int) on;
+			}
 		}
 		n_cur -= removed;
 		if (++iter >= SSC_ITER_CAP) { cap = 1; break; }
@@ -262,28 +266,36 @@ k_stack_warp(StackParams p, unsigned int n_tiles, unsigned int tiles_per_row, in
 	const unsigned int sbase = (unsigned int) __cvta_generic_to_shared(stage);
 	const unsigned long long fstride = (unsigned long long) b.frame_stride * sizeof(WORD);
 
+	// stage a tile: thread -> (pair tid % 8, frames tid / 8, tid / 8 + 32, ...), 4-byte asynchronous copies.
+	// The next tile is requested as soon as the columns are in registers, so it lands under the sort and the fit.
+	auto issue_tile = [&](const unsigned int t) {
+		const unsigned int trow = t / tiles_per_row;
+		const int tx2_0 = (int) (t - trow * tiles_per_row) * WARP_PAIRS;
+		const int tlayer = (int) (trow / (unsigned int) b.out_rows);
+		const int tRr = b.out_row0 + (int) (trow - (unsigned int) tlayer * (unsigned int) b.out_rows);
+		const int tsrow = b.row_order == SSC_ROWS_SER ? b.height - 1 - tRr : tRr;
+		const size_t trow_words = ((size_t) tlayer * b.layer_stride + (size_t) (tsrow - b.buf_row0) * W) >> 1;
+		const int j = tid & (WARP_PAIRS - 1);
+		int x2 = tx2_0 + j;
+		if (x2 >= W2) x2 = W2 - 1;			// ragged row end: a duplicate, never written back
+		const char *src = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames) + trow_words + x2);
+		for (int f = tid >> 3; f < N; f += 32)
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::
+					"r"(sbase + (unsigned int) ((f * WARP_PITCH + j) * (int) sizeof(unsigned int))),
+					"l"(src + (unsigned long long) f * fstride) : "memory");
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	if (blockIdx.x < n_tiles) issue_tile(blockIdx.x);
+
 	for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 		const unsigned int row = tile / tiles_per_row;
 		const int x2_0 = (int) (tile - row * tiles_per_row) * WARP_PAIRS;
 		const int layer = (int) (row / (unsigned int) b.out_rows);
 		const int rr = (int) (row - (unsigned int) layer * (unsigned int) b.out_rows);
 		const int Rr = b.out_row0 + rr;				// result storage row (stacking.c:731,1600)
-		const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - Rr : Rr;
-		const size_t row_words = ((size_t) layer * b.layer_stride + (size_t) (srow - b.buf_row0) * W) >> 1;
 
-		// ---- 1. stage the tile: thread -> (pair tid % 8, frames tid / 8, tid / 8 + 32, ...) ----
-		{
-			const int j = tid & (WARP_PAIRS - 1);
-			int x2 = x2_0 + j;
-			if (x2 >= W2) x2 = W2 - 1;			// ragged row end: a duplicate, never written back
-			const char *src = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames) + row_words + x2);
-			for (int f = tid >> 3; f < N; f += 32)
-				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::
-						"r"(sbase + (unsigned int) ((f * WARP_PITCH + j) * (int) sizeof(unsigned int))),
-						"l"(src + (unsigned long long) f * fstride) : "memory");
-			asm volatile("cp.async.commit_group;" ::: "memory");
-			asm volatile("cp.async.wait_group 0;" ::: "memory");
-		}
+		// ---- 1. the tile's samples (requested a tile ago, see issue_tile) ----
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncthreads();
 
 		// ---- normalization in place (stacking.c:1635-1652, :750-764), a rolled loop over the tile ----
@@ -317,6 +329,7 @@ k_stack_warp(StackParams p, unsigned int n_tiles, unsigned int tiles_per_row, in
 			v[r] = f < N ? stage[f * WARP_PITCH + warp] : 0xFFFFFFFFu;
 		}
 		__syncthreads();					// the staging tile may be overwritten now
+		if (tile + gridDim.x < n_tiles) issue_tile(tile + gridDim.x);
 
 		// ---- 2. sort: lane l ends up with sorted samples [l R, (l + 1) R) of both pixels ----
 		warp_sort<R>(v, lane);

@@ -92,13 +92,28 @@ k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
 		outside += in ? 0u : 1u;
 		seen |= a;
 	};
-	auto count8 = [&](const uint4 &v) {
-		const unsigned int w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-		for (int k = 0; k < 4; k++) {
-			count1(w[k] & 0xFFFFu);
-			count1(w[k] >> 16);
+	// Two samples at a time: with base2 = base | base << 16, t = w - base2 has both 11-bit window
+	// offsets in place exactly when both samples are inside the window (a low half below the window
+	// borrows and leaves bits >= 11 set in it, because base <= 65536 - HIST_WIN), so the common case of
+	// an astronomical background costs one subtraction and one test per pair on top of the two atomics.
+	const unsigned int base2 = base | (base << 16);
+	unsigned int *const win = sh + 32768;
+	auto count2 = [&](unsigned int w) {
+		const unsigned int t = w - base2;
+		if ((t & ((0xFFFFu ^ (HIST_WIN - 1)) * 0x10001u)) == 0) {
+			atomicAdd(win + (t & 0xFFFFu), 1u);
+			atomicAdd(win + (t >> 16), 1u);
+			seen |= w;
+		} else {
+			count1(w & 0xFFFFu);
+			count1(w >> 16);
 		}
+	};
+	auto count8 = [&](const uint4 &v) {
+		count2(v.x);
+		count2(v.y);
+		count2(v.z);
+		count2(v.w);
 	};
 	auto flush_full = [&]() {	// non-zero 16-bit counters -> the global 32-bit histogram
 		__syncthreads();
@@ -162,7 +177,7 @@ k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
 		if (c) atomicAdd(&gh[base + i], c);
 	}
 	// word 65537: "layer 0 of this band has a sample > 255" (consumed by k_other_layers_gt255)
-	if (seen > 255u) atomicOr(&any_gt255, 1u);
+	if ((seen & 0xFFFFu) > 255u || (seen >> 16) > 255u) atomicOr(&any_gt255, 1u);	// (seen collects packed pairs and single samples)
 	__syncthreads();
 	if (tid == 0 && any_gt255) atomicOr(&gh[65537], 1u);
 }

@@ -173,7 +173,12 @@ def test_histogram_wide_range_flushes_mid_stream(gpu, port, refrun):
         assert got[f, :65536].sum() == h * w
         loc, sc, nv, ng = refrun.frame_stats(fr[f])
         assert st[0, f] == loc, f                                      # a bin value: exact
-        assert abs(st[1, f] - sc) <= 1e-11 * abs(sc), f
+        # the reference adds its biweight terms sample by sample in FP64 (statistics.c:136-145): over 16 M
+        # samples that sum drifts by up to ~n eps (1.7e-11 measured on the disc frame; a long double
+        # evaluation agrees with the histogram form, count x term per bin, to 2e-16)
+        assert abs(st[1, f] - sc) <= 1e-9 * abs(sc), f
+        hloc, hsc, hnv, _ = port.frame_stats_hist(fr[f])
+        assert st[0, f] == hloc and st[1, f] == hsc and st[2, f] == hnv   # same form, same order: bit-identical
         assert st[2, f] == nv and st[3, f] == ng
     # band decomposition at this size: three uneven bands add up to the same histograms
     hist2 = torch.zeros_like(hist)
@@ -185,7 +190,8 @@ def test_histogram_wide_range_flushes_mid_stream(gpu, port, refrun):
 
 def test_cfg3_frame_statistics_full_size(gpu, refrun):
     """Location / scale of full 6000x4000 RGB frames of configs[2] against the reference's sort-based
-    statistics() (statistics.c:277-290): location exact, scale within 1e-11 relative; and the
+    statistics() (statistics.c:277-290): location exact, scale within 1e-9 relative (the reference's own
+    sample-by-sample sum drifts by ~n eps over 24 M samples, see the wide-range test); and the
     coefficients that follow."""
     n, c, h, w = 2, 3, 4000, 6000
     fr = synth_band(gpu, n, c, h, w, 0, h, 0)
@@ -202,7 +208,7 @@ def test_cfg3_frame_statistics_full_size(gpu, refrun):
     ref = [refrun.frame_stats(host_u16(fr[f])) for f in range(n)]
     for f in range(n):
         assert st[0, f] == ref[f][0]
-        assert abs(st[1, f] - ref[f][1]) <= 1e-11 * ref[f][1]
+        assert abs(st[1, f] - ref[f][1]) <= 1e-9 * ref[f][1]
         assert st[2, f] == ref[f][2] and st[3, f] == ref[f][3]
     cf = coeff.cpu().numpy()
     assert cf[1, 0] == 1.0 and cf[1, 1] == ref[0][0] / ref[1][0]       # mul = L_ref / L_i (stacking.c:116-120)

@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "siril-0.9_b200", "csrc", "ssc_sortnet.h")
 def networks():
     text = open(HEADER).read()
     nets = {}
-    for m in re.finditer(r"#define SSC_SORTNET_(\d+)((?:.*\\\n)*.*\n)", text):
+    for m in re.finditer(r"#define SSC_SORTNET_(\d+) ((?:.*\\\n)*.*\n)", text):
         nets[int(m.group(1))] = [(int(a), int(b)) for a, b in re.findall(r"SSC_CE\((\d+),(\d+)\)", m.group(2))]
     return nets
 
@@ -25,6 +25,39 @@ def apply_network(ces, v):
         lo, hi = np.minimum(v[a], v[b]), np.maximum(v[a], v[b])
         v[a], v[b] = lo, hi
     return v
+
+
+def pruned_networks():
+    """SSC_SORTNET_<n>_SIGMA: [(op, a, b)] with op in CE / MIN / MAX."""
+    text = open(HEADER).read()
+    nets = {}
+    for m in re.finditer(r"#define SSC_SORTNET_(\d+)_SIGMA ((?:.*\\\n)*.*\n)", text):
+        nets[int(m.group(1))] = [(op, int(a), int(b)) for op, a, b in re.findall(r"SSC_(CE|MIN|MAX)\((\d+),(\d+)\)", m.group(2))]
+    return nets
+
+
+@pytest.mark.parametrize("n", [32, 64])
+def test_pruned_sigma_networks_place_the_ranks_the_kernel_reads(n):
+    """The register sigma clipping (ssc_stack_fast.cu) reads ranks 0..2, n/2-3..n/2+1 and n-6..n-1 only; the
+    pruned network (dead comparator halves removed, tools/gen_sortnet.py) must leave exactly the sorted
+    values there: all threshold (0-1) inputs in random order, heavy ties, and random u16 columns."""
+    ops = pruned_networks()[n]
+    full = networks()[n]
+    n_ops = sum(2 if op == "CE" else 1 for op, _, _ in ops)
+    assert n_ops == {32: 332, 64: 888}[n] and n_ops < 2 * len(full)
+    ranks = [0, 1, 2] + list(range(n // 2 - 3, n // 2 + 2)) + list(range(n - 6, n))
+    rng = np.random.default_rng(n)
+    cols = [rng.permutation(np.r_[np.zeros(n - t, np.int64), np.ones(t, np.int64)]) for t in range(n + 1) for _ in range(40)]
+    cols += [rng.integers(0, 4, n) for _ in range(500)] + [rng.integers(0, 65536, n) for _ in range(2000)]
+    v = np.array(cols).T.copy()                                       # [n, columns]
+    want = np.sort(v, axis=0)
+    for op, a, b in ops:
+        lo, hi = np.minimum(v[a], v[b]), np.maximum(v[a], v[b])
+        if op in ("CE", "MIN"):
+            v[a] = lo
+        if op in ("CE", "MAX"):
+            v[b] = hi
+    assert np.array_equal(v[ranks], want[ranks])
 
 
 def test_header_has_the_three_networks():
