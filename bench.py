@@ -48,7 +48,7 @@ DOMINANT = {
     "cfg2": "k_stack_fast<32,true,MEDIAN> (K2: register sorting network, truncating median)",
     "cfg3": "k_stack_fast<64,true,SIGMA_REG> (K3: normalize + sigma-clip + mean, register sorting network)",
     "cfg4": "k_stack_mid<256,64> (K3: normalize + sort in shared memory + winsorized clipping + mean)",
-    "cfg5": "k_stack_mid<1024,16> + k_tail_spilled (K3: sort in shared memory, linear-fit clipping from spilled columns)",
+    "cfg5": "k_stack_warp<32> (K3: one warp per pixel pair, register bitonic sort over the lanes, exact-sums linear-fit clipping)",
 }
 
 
@@ -229,6 +229,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None, help="steps of the end-to-end leg (default min(steps, 5))")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: the library's own kernels over NVLink peer memory (default) or torch.distributed (NCCL) collectives")
     ap.add_argument("--small", action="store_true", help="1/16 of the frame area (debug only; not a bench value)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -282,7 +284,21 @@ def main():
         scratch = torch.empty((n, 65536), dtype=torch.int32, device=dev)
         stats = torch.empty((4, n), dtype=torch.float64, device=dev)
         hband = pkg.dev.band(frames.data_ptr(), n, c, h, w, out_row0=src0, out_rows=rows, buf_row0=src0, buf_rows=rows)
-    shard_stats = bool(norm) and world > 1 and n % world == 0   # reduce-scatter the histograms, IKSS on n / world frames per rank
+    # ---- N > 1: the exchanges.  Default: the library's peer group -- every rank maps every other rank's block
+    # (cudaIpc handles, all-gathered once here) and K4 / K5 / K6 exchange through it inside the kernels.
+    group = None
+    if world > 1 and args.exchange == "peer":
+        group = pkg.PeerGroup(world, rank, n)
+        mine = torch.frombuffer(bytearray(group.export()), dtype=torch.uint8).to(dev)
+        allh = torch.empty((world, pkg.PEER_HANDLE_BYTES), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh.view(-1), mine)
+        allh = allh.cpu().numpy()
+        for r in range(world):
+            group.import_(r, allh[r].tobytes())
+        group.connect()
+        counters_local = torch.zeros(pkg.N_COUNTERS, dtype=torch.int64, device=dev)
+        dist.barrier()
+    shard_stats = group is None and bool(norm) and world > 1 and n % world == 0   # reduce-scatter the histograms, IKSS on n / world frames per rank
     n_loc = n // world if shard_stats else n
     if shard_stats:
         hist_loc = torch.empty((n_loc, pkg.HIST_STRIDE), dtype=torch.int32, device=dev)
@@ -300,8 +316,10 @@ def main():
             maxim.zero_()
             pkg.dev.sum_accumulate(band, acc.data_ptr(), maxim.data_ptr(), sp)
             if ev: ev[1].record(stream)
-            if world > 1:
-                dist.all_reduce(maxim, op=dist.ReduceOp.MAX)        # stacking.c:311-313: one global max
+            if group is not None:
+                group.max_combine(maxim.data_ptr(), sp)            # stacking.c:311-313: one global max
+            elif world > 1:
+                dist.all_reduce(maxim, op=dist.ReduceOp.MAX)
             if ev: ev[2].record(stream)
             pkg.dev.sum_finish(acc.data_ptr(), c * rows * w, maxim.data_ptr(), out.data_ptr(), sp)
             if ev: ev[3].record(stream)
@@ -312,7 +330,15 @@ def main():
             if ev: ev[3].record(stream)
             return
         counters.zero_()
-        if norm:
+        if norm and group is not None:
+            # K4 adds this band's counts straight into the owners' histograms (frame f: rank f % world), K5 runs on
+            # the owned frames once all bands arrived and stores the statistics into every rank's table, K6 waits
+            # for all owners: no collective call, no host in between (csrc/ssc_peer.cu)
+            group.histogram_scatter(hband, True, sp)
+            if ev: ev[1].record(stream)
+            group.ikss_gather(n, scratch.data_ptr(), sp)
+            group.norm_coeffs_gathered(n, 0, norm, coeff.data_ptr(), status.data_ptr(), None, sp)
+        elif norm:
             hist.zero_()
             pkg.dev.histogram(hband, hist.data_ptr(), sp)
             if shard_stats:
@@ -333,6 +359,13 @@ def main():
         elif ev:
             ev[1].record(stream)
         if ev: ev[2].record(stream)
+        if group is not None:
+            counters_local.zero_()
+            pkg.dev.stack_mean(band, out.data_ptr(), counters_local.data_ptr(), rej, sig, norm, coeff.data_ptr() if norm else None,
+                               stream=sp)
+            if ev: ev[3].record(stream)
+            group.counters_combine(counters_local.data_ptr(), counters.data_ptr(), sp)
+            return
         pkg.dev.stack_mean(band, out.data_ptr(), counters.data_ptr(), rej, sig, norm, coeff.data_ptr() if norm else None,
                            stream=sp)
         if ev: ev[3].record(stream)
@@ -372,16 +405,33 @@ def main():
     guard, cap = int(counters[6].item()), int(counters[7].item())
 
     # ---- end to end: pinned host frames -> result on the host, copies inside the timer ----
+    # One operator call on the whole image, as a Siril host makes it.  N > 1: ssc_set_devices(0..N-1) and the SAME
+    # single call from rank 0 -- the library splits the image over the GPUs itself (one host thread and three
+    # streams per device, NVLink exchanges between the devices); the other ranks only hold the barrier.
     e2e = None
     if not args.no_e2e:
         e2e_steps = args.e2e_steps if args.e2e_steps is not None else min(args.steps, 5)
-        host = torch.empty((n, c, rows, w), dtype=torch.int16, pin_memory=True)
-        host.copy_(frames)
-        torch.cuda.synchronize()
-        h2d_bytes = host.numel() * 2
-        d2h_bytes = c * rows * w * 2
-        if world == 1:
+        h2d_bytes = n * c * h * w * 2
+        d2h_bytes = c * h * w * 2
+        e2e_ms, r = 0.0, None
+        e2e_api = "ssc_stack_%s (operator layer, whole image%s)" % (
+            dict(sum="summing", median="median", mean="mean_with_rejection")[op],
+            "" if world == 1 else ", ssc_set_devices(0..%d), one call from rank 0" % (world - 1))
+        if rank == 0:
+            host = torch.empty((n, c, h, w), dtype=torch.int16, pin_memory=True)
+            if world == 1:
+                host.copy_(frames)
+            else:                                           # the other bands, regenerated here (counter-based generator)
+                for rr in range(world):
+                    b0, br = band_rows(h, world, rr)
+                    s0 = h - (b0 + br) if ro == 1 else b0
+                    tmp = torch.empty((n, c, br, w), dtype=torch.int16, device=dev)
+                    pkg.dev.synth_frames(tmp.data_ptr(), n, c, br, w, 0, s0, h, cfg["kind"], SEED, sp)
+                    host[:, :, s0:s0 + br, :].copy_(tmp)
+                    del tmp
+            torch.cuda.synchronize()
             seq = pkg.Sequence([host[i].numpy().view(np.uint16) for i in range(n)], row_order=ro)
+            pkg.set_devices(list(range(world)))
 
             def e2e_step():
                 if op == "sum":
@@ -389,38 +439,26 @@ def main():
                 if op == "median":
                     return pkg.stack_median(seq)
                 return pkg.stack_mean_with_rejection(seq, rej, sig, norm, want_coeff=False)
-            e2e_api = "ssc_stack_%s (operator layer, whole image)" % dict(sum="summing", median="median", mean="mean_with_rejection")[op]
-        else:
-            host_out = torch.empty((c, rows, w), dtype=torch.int16, pin_memory=True)
-
-            def e2e_step():
-                frames.copy_(host, non_blocking=True)
-                step()
-                host_out.copy_(out, non_blocking=True)
-                return None
-            e2e_api = "per-rank band pipeline: pinned H2D + ssc_dev_* + D2H"
-        for _ in range(2):
-            r = e2e_step()
+            for _ in range(2):
+                r = e2e_step()
+            t_wall0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                r = e2e_step()
+            e2e_ms = (time.perf_counter() - t_wall0) * 1e3 / max(e2e_steps, 1)
+            pkg.set_devices([0])
         sync_all()
-        t_wall0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            r = e2e_step()
-        sync_all()
-        e2e_ms = (time.perf_counter() - t_wall0) * 1e3 / max(e2e_steps, 1)
-        te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_ms = float(te.item())
         e2e_parity, op_timing = None, None
-        if world == 1 and r is not None:
-            e2e_parity = bool(np.array_equal(r.data, out.cpu().numpy().view(np.uint16)))
+        if rank == 0 and r is not None:
+            mine = r.data[:, row0:row0 + rows, :]           # this rank's band of the operator's image
+            e2e_parity = bool(np.array_equal(mine, out.cpu().numpy().view(np.uint16)))
             if op == "mean":
                 e2e_parity = e2e_parity and bool(np.array_equal(r.irej, irej))
-            op_timing = dict(h2d_ms=r.t_h2d_ms, device_ms=r.t_device_ms, d2h_ms=r.t_d2h_ms, total_ms=r.t_total_ms)
-        e2e = dict(value=samples_total / 1e9 / (e2e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_bytes * world,
-                   d2h_bytes_per_step=d2h_bytes * world, ms_per_step=e2e_ms, steps=e2e_steps, api=e2e_api,
-                   operator_timing_ms=op_timing, matches_device_path=e2e_parity)
-        del host
+            op_timing = dict(h2d_ms=r.t_h2d_ms, tail_after_upload_ms=r.t_device_ms, total_ms=r.t_total_ms)
+            e2e = dict(value=samples_total / 1e9 / (e2e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_bytes,
+                       d2h_bytes_per_step=d2h_bytes, ms_per_step=e2e_ms, steps=e2e_steps, api=e2e_api,
+                       operator_timing_ms=op_timing, matches_device_path=e2e_parity)
+            del host, seq, r
+            pkg.release_workspace()
 
     clocks = sampler.stop() if sampler else None
 
@@ -494,6 +532,8 @@ def main():
             dtype="u16 samples, f64 clipping/normalization arithmetic" if op == "mean" else "u16", data="synthetic",
             config=dict(workload=cfg["name"], frames=n, width=w, height=h, channels=c,
                         parallelism="row bands x%d" % world,
+                        exchange=(None if world == 1 else ("libsiril_stack_cuda peer group (kernels over NVLink peer memory)"
+                                                           if group is not None else "torch.distributed NCCL collectives")),
                         l2=("inputs (%.1f GB) exceed L2 (126 MB): no flush needed" % (in_bytes / 1e9) if flush is None else
                             "inputs (%.0f MB) fit L2: a 256 MB buffer is written between timed steps (outside the per-step events)" % (in_bytes / world / 1e6)),
                         seed=hex(SEED), rejection_counters=irej.tolist(), guard_fired=guard, cap_hit=cap),
@@ -504,6 +544,10 @@ def main():
             step_hbm_frac=(full_stack + full_stats) / world / (ms_step / 1e3) / 1e9 / peak,
             e2e=e2e, gpu_launches=launches * args.steps, clocks=clocks, parity=parity, cpu_baseline=cpu)
         _emit(line)
+    if group is not None:
+        assert group.status(sp) == 0, "a peer exchange timed out"
+        dist.barrier()
+        group.close()
     if world > 1:
         dist.destroy_process_group()
 

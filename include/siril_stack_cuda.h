@@ -270,6 +270,48 @@ int ssc_dev_ikss(const uint32_t *hist, int n_frames, double *stats, uint32_t *sc
 int ssc_dev_norm_coeffs(const double *stats, int n_frames, int ref_image, int mode,
 		double *coeff, int *status, void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* Several GPUs: the exchanges of the path as kernels over NVLink peer memory */
+/* ------------------------------------------------------------------------- */
+/* The image is split in row bands, one per GPU ("rank"); what the reference keeps in shared
+ * variables of its OpenMP threads becomes three small exchanges: the per-frame
+ * histograms add up before the IKSS (stacking.c:166-187 computes them per frame on whole images),
+ * stack_summing's maximum (stacking.c:311-313) and the rejection counters (:1796-1802).  Every rank
+ * owns a block of device memory that all others map; the kernels add / store into it directly, no
+ * host in between.  One process per GPU: ssc_peer_export / ssc_peer_import (cudaIpc handles, passed
+ * around by the host's own means); one process driving several GPUs: ssc_peer_attach_local.  All
+ * ranks make the same calls in the same order; `stream` as in the device layer. */
+typedef struct ssc_peer_group ssc_peer_group;
+#define SSC_PEER_MAX 64
+#define SSC_PEER_HANDLE_BYTES 64
+#define SSC_PEER_TIMEOUT (-110)	/* a rank waited ~10 s for a peer that never arrived (ssc_peer_status) */
+/* on the current device; n_frames_max bounds n_frames of the later calls */
+int ssc_peer_create(int world, int rank, int n_frames_max, ssc_peer_group **out);
+int ssc_peer_export(ssc_peer_group *g, void *handle64);
+int ssc_peer_import(ssc_peer_group *g, int peer_rank, const void *handle64);
+int ssc_peer_attach_local(ssc_peer_group *g, int peer_rank, ssc_peer_group *other);
+int ssc_peer_connect(ssc_peer_group *g);		/* after every peer was imported / attached */
+int ssc_peer_destroy(ssc_peer_group *g);
+int ssc_peer_world(const ssc_peer_group *g);
+int ssc_peer_rank(const ssc_peer_group *g);
+int ssc_peer_status(ssc_peer_group *g, void *stream);	/* 0 or SSC_PEER_TIMEOUT; synchronises the stream */
+const char *ssc_peer_last_error(void);
+/* K4 fused with the reduce-scatter of the histograms: frame f is analysed by rank f % world and this
+ * band's counts are added straight into that rank's histogram.  last_piece = 0 when more row pieces
+ * of this rank's band follow in the same exchange. */
+int ssc_dev_histogram_scatter(const ssc_band *band, ssc_peer_group *g, int last_piece, void *stream);
+/* K5 on this rank's frames once all ranks' counts are in, then the all-gather of the 4 statistics per
+ * frame.  scratch: device uint32_t [ceil(n_frames / world)][65536]. */
+int ssc_dev_ikss_gather(ssc_peer_group *g, int n_frames, uint32_t *scratch, void *stream);
+/* K6 once every owner's statistics are here: identical coefficients on every rank.  stats_out (device
+ * double[4][n_frames]) may be NULL. */
+int ssc_dev_norm_coeffs_gathered(ssc_peer_group *g, int n_frames, int ref_image, int mode, double *coeff,
+		int *status, double *stats_out, void *stream);
+/* total (device uint64_t[SSC_COUNTERS]) = sum over the ranks of local (stacking.c:1796-1802) */
+int ssc_dev_counters_combine(ssc_peer_group *g, const uint64_t *local, uint64_t *total, void *stream);
+/* *maxim (device uint64_t) = max over the ranks, between K1 and K1b (stacking.c:311-313, 328-330) */
+int ssc_dev_max_combine(ssc_peer_group *g, unsigned long long *maxim, void *stream);
+
 /* Counter-based synthetic frames for benchmarks and large-size
  * property tests: fills device WORD [n_frames][layers][rows][width] with storage
  * rows [row0, row0+rows) of frames first_frame.. of a full_height-row image; every

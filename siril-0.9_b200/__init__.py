@@ -128,6 +128,10 @@ EXPORTS = [
     "ssc_version", "ssc_dev_stack_median", "ssc_dev_stack_mean", "ssc_dev_sum_accumulate",
     "ssc_dev_sum_finish", "ssc_dev_stack_extreme", "ssc_dev_histogram", "ssc_dev_ikss", "ssc_dev_norm_coeffs",
     "ssc_dev_synth_frames",
+    "ssc_peer_create", "ssc_peer_export", "ssc_peer_import", "ssc_peer_attach_local", "ssc_peer_connect",
+    "ssc_peer_destroy", "ssc_peer_world", "ssc_peer_rank", "ssc_peer_status", "ssc_peer_last_error",
+    "ssc_dev_histogram_scatter", "ssc_dev_ikss_gather", "ssc_dev_norm_coeffs_gathered",
+    "ssc_dev_counters_combine", "ssc_dev_max_combine",
 ]
 
 _lib.ssc_last_error.restype = C.c_char_p
@@ -154,6 +158,20 @@ _lib.ssc_dev_ikss.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_v
 _lib.ssc_dev_norm_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.ssc_dev_synth_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_uint64, C.c_void_p]
+_lib.ssc_peer_last_error.restype = C.c_char_p
+_lib.ssc_peer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+_lib.ssc_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+_lib.ssc_peer_import.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+_lib.ssc_peer_attach_local.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+_lib.ssc_peer_connect.argtypes = [C.c_void_p]
+_lib.ssc_peer_destroy.argtypes = [C.c_void_p]
+_lib.ssc_peer_status.argtypes = [C.c_void_p, C.c_void_p]
+_lib.ssc_dev_histogram_scatter.argtypes = [C.POINTER(Band), C.c_void_p, C.c_int, C.c_void_p]
+_lib.ssc_dev_ikss_gather.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+_lib.ssc_dev_norm_coeffs_gathered.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]
+_lib.ssc_dev_counters_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+_lib.ssc_dev_max_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 _libc = C.CDLL(None)
 _libc.free.argtypes = [C.c_void_p]
 
@@ -437,3 +455,71 @@ class dev:
         full_height = rows if full_height is None else full_height
         dev._check(_lib.ssc_dev_synth_frames(frames_ptr, n_frames, layers, rows, width, first_frame, row0,
                                              full_height, kind, seed, stream), "ssc_dev_synth_frames")
+
+
+PEER_HANDLE_BYTES = 64
+PEER_TIMEOUT = -110
+
+
+class PeerError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        msg = _lib.ssc_peer_last_error()
+        super().__init__("%s returned %d: %s" % (where, code, msg.decode() if msg else ""))
+
+
+class PeerGroup:
+    """ssc_peer_group: this GPU's end of the NVLink exchanges (include/siril_stack_cuda.h).  Created on the
+    current CUDA device.  One process per GPU: export() / import_() the 64-byte handles (the host moves them,
+    e.g. with torch.distributed.all_gather); several GPUs in one process: attach_local()."""
+
+    def __init__(self, world, rank, n_frames_max):
+        h = C.c_void_p()
+        rc = _lib.ssc_peer_create(world, rank, n_frames_max, C.byref(h))
+        if rc:
+            raise PeerError(rc, "ssc_peer_create")
+        self.h, self.world, self.rank = h, world, rank
+
+    @staticmethod
+    def _check(rc, where):
+        if rc:
+            raise PeerError(rc, where)
+
+    def export(self):
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        self._check(_lib.ssc_peer_export(self.h, buf), "ssc_peer_export")
+        return buf.raw
+
+    def import_(self, peer_rank, handle):
+        self._check(_lib.ssc_peer_import(self.h, peer_rank, C.create_string_buffer(bytes(handle), PEER_HANDLE_BYTES)),
+                    "ssc_peer_import")
+
+    def attach_local(self, peer_rank, other):
+        self._check(_lib.ssc_peer_attach_local(self.h, peer_rank, other.h), "ssc_peer_attach_local")
+
+    def connect(self):
+        self._check(_lib.ssc_peer_connect(self.h), "ssc_peer_connect")
+
+    def histogram_scatter(self, band, last_piece=True, stream=0):
+        self._check(_lib.ssc_dev_histogram_scatter(C.byref(band), self.h, int(last_piece), stream), "ssc_dev_histogram_scatter")
+
+    def ikss_gather(self, n_frames, scratch_ptr, stream=0):
+        self._check(_lib.ssc_dev_ikss_gather(self.h, n_frames, scratch_ptr, stream), "ssc_dev_ikss_gather")
+
+    def norm_coeffs_gathered(self, n_frames, ref_image, mode, coeff_ptr, status_ptr=None, stats_ptr=None, stream=0):
+        self._check(_lib.ssc_dev_norm_coeffs_gathered(self.h, n_frames, ref_image, mode, coeff_ptr, status_ptr, stats_ptr,
+                                                      stream), "ssc_dev_norm_coeffs_gathered")
+
+    def counters_combine(self, local_ptr, total_ptr, stream=0):
+        self._check(_lib.ssc_dev_counters_combine(self.h, local_ptr, total_ptr, stream), "ssc_dev_counters_combine")
+
+    def max_combine(self, maxim_ptr, stream=0):
+        self._check(_lib.ssc_dev_max_combine(self.h, maxim_ptr, stream), "ssc_dev_max_combine")
+
+    def status(self, stream=0):
+        return _lib.ssc_peer_status(self.h, stream)
+
+    def close(self):
+        if self.h:
+            _lib.ssc_peer_destroy(self.h)
+            self.h = None

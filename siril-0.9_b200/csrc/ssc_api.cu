@@ -3,7 +3,9 @@
 // the operator layer (stack_method-compatible entry points that move a bound
 // in-memory sequence through the GPUs band by band).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <future>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -281,6 +283,9 @@ struct Job {
 };
 
 struct Piece { int row0, rows; };	// result storage rows
+// One launch of a stacking kernel: a layer of a row chunk of a piece.  The frames of a chunk are uploaded,
+// stacked and downloaded as a unit, so the three stages of consecutive units overlap.
+struct Unit { int piece, layer, row0, rows; };
 
 // Device buffers are kept between operator calls (a 9 GB cudaMalloc/cudaFree pair costs far more
 // than the stack itself); ssc_release_workspace() returns them.
@@ -299,13 +304,29 @@ struct Buf {
 };
 
 struct DevCache {
-	cudaStream_t stream = nullptr;
-	Buf frames, out, hist, scratch, acc, stats, coeff, status, shifts, counters, maxim;
+	cudaStream_t copy = nullptr, comp = nullptr, out = nullptr;	// upload, kernels, download
+	Buf frames, outb, hist, scratch, acc, stats, coeff, status, shifts, counters, maxim, flags;
+	std::vector<cudaEvent_t> events;
+	ssc_peer_group *group = nullptr;	// this device's end of the NVLink exchanges (several devices only)
+	std::vector<int> group_ids;
+	int group_frames = 0;
 	void release() {
-		Buf *all[] = {&frames, &out, &hist, &scratch, &acc, &stats, &coeff, &status, &shifts, &counters, &maxim};
+		Buf *all[] = {&frames, &outb, &hist, &scratch, &acc, &stats, &coeff, &status, &shifts, &counters, &maxim, &flags};
 		for (Buf *b : all) b->release();
-		if (stream) cudaStreamDestroy(stream);
-		stream = nullptr;
+		for (cudaEvent_t e : events) cudaEventDestroy(e);
+		events.clear();
+		if (group) ssc_peer_destroy(group);
+		group = nullptr;
+		for (cudaStream_t *s : {&copy, &comp, &out}) { if (*s) cudaStreamDestroy(*s); *s = nullptr; }
+	}
+	int event(size_t i, cudaEvent_t &e) {
+		while (events.size() <= i) {
+			cudaEvent_t n;
+			if (cudaEventCreateWithFlags(&n, cudaEventDisableTiming) != cudaSuccess) return SSC_ERR_CUDA;
+			events.push_back(n);
+		}
+		e = events[i];
+		return SSC_OK;
 	}
 };
 std::map<int, DevCache> g_cache;	// by device id; operator calls are serialised (g_op_mu)
@@ -314,20 +335,24 @@ void *g_pinned = nullptr;		// pinned bounce buffer for the result rows
 size_t g_pinned_cap = 0;
 
 struct Dev {
-	int id = 0;
-	cudaStream_t stream = nullptr;
+	int id = 0, index = 0;
+	DevCache *dc = nullptr;
 	std::vector<Piece> pieces;
+	std::vector<Unit> units;
 	int max_rows = 0, max_buf_rows = 0;
 	WORD *frames = nullptr, *out = nullptr;
-	uint32_t *hist = nullptr, *scratch = nullptr, *acc = nullptr;
+	uint32_t *hist = nullptr, *scratch = nullptr, *acc = nullptr, *flags = nullptr;
 	double *stats = nullptr, *coeff = nullptr;
 	int *status = nullptr, *shifts = nullptr;
-	unsigned long long *counters = nullptr, *maxim = nullptr;
-	bool resident = false;
+	unsigned long long *counters = nullptr, *maxim = nullptr;	// counters: [layers][SSC_COUNTERS]
+	ssc_peer_group *group = nullptr;
+	int rc = SSC_OK;
+	std::string err;
+	double t_h2d = 0, t_dev = 0, t_d2h = 0;
 };
 
-// the source storage rows a piece needs: its own rows plus the reach of the y shifts
-void source_rows(const Job &job, const Piece &pc, int H, int &buf_row0, int &buf_rows) {
+// the source storage rows a range of result rows needs: its own rows plus the reach of the y shifts
+void source_rows(const Job &job, int row0, int rows, int H, int &buf_row0, int &buf_rows) {
 	int min_sy = 0, max_sy = 0;
 	if (job.op != OP_MEDIAN && job.seq->have_reg)
 		for (int idx : job.images) {
@@ -338,12 +363,12 @@ void source_rows(const Job &job, const Piece &pc, int H, int &buf_row0, int &buf
 	const bool ser = job.seq->view.row_order == SSC_ROWS_SER;
 	if (frame_walker(job.op)) {
 		// fits row y reads fits row y - sy; fits row = storage row (FITS) or H-1-row (SER)
-		int flo = pc.row0 - max_sy, fhi = pc.row0 + pc.rows - min_sy;
+		int flo = row0 - max_sy, fhi = row0 + rows - min_sy;
 		if (ser) { lo = H - fhi; hi = H - flo; } else { lo = flo; hi = fhi; }
 	} else if (!ser) {
-		lo = pc.row0 - max_sy; hi = pc.row0 + pc.rows - min_sy;	// storage row R - sy
+		lo = row0 - max_sy; hi = row0 + rows - min_sy;	// storage row R - sy
 	} else {
-		lo = H - (pc.row0 + pc.rows) + min_sy; hi = H - pc.row0 + max_sy;	// storage row (H-1-R) + sy
+		lo = H - (row0 + rows) + min_sy; hi = H - row0 + max_sy;	// storage row (H-1-R) + sy
 	}
 	lo = std::max(lo, 0);
 	hi = std::min(hi, H);
@@ -352,33 +377,277 @@ void source_rows(const Job &job, const Piece &pc, int H, int &buf_row0, int &buf
 	buf_rows = hi - lo;
 }
 
-int upload_piece(const Job &job, Dev &d, const Piece &pc, ssc_band &band) {
-	const ssc_sequence_view &v = job.seq->view;
-	const int W = v.rx, H = v.ry, C = v.nb_layers, N = (int) job.images.size();
-	int buf_row0, buf_rows;
-	source_rows(job, pc, H, buf_row0, buf_rows);
+// what a device thread needs to know about the call
+struct Plan {
+	const Job *job;
+	int W, H, C, N, G;
+	bool need_norm, shifted, strided;
+	size_t host_stride;		// bytes between consecutive frames on the host when they are equally spaced
+	WORD *result, *landing;
+	size_t plane;
+	const std::atomic<bool> *cancel;
+	std::shared_future<void> result_ready;	// the result's pages have been touched (see run_job)
+};
+
+// the device-resident band of a piece
+void piece_band(const Plan &pl, const Dev &d, const Piece &pc, ssc_band &band) {
+	const ssc_sequence_view &v = pl.job->seq->view;
+	int b0, br;
+	source_rows(*pl.job, pc.row0, pc.rows, pl.H, b0, br);
 	band.frames = d.frames;
-	band.layer_stride = (size_t) buf_rows * W;
-	band.frame_stride = band.layer_stride * C;
-	band.n_frames = N;
-	band.layers = C;
-	band.width = W;
-	band.height = H;
-	band.buf_row0 = buf_row0;
-	band.buf_rows = buf_rows;
+	band.layer_stride = (size_t) br * pl.W;
+	band.frame_stride = band.layer_stride * pl.C;
+	band.n_frames = pl.N;
+	band.layers = pl.C;
+	band.width = pl.W;
+	band.height = pl.H;
+	band.buf_row0 = b0;
+	band.buf_rows = br;
 	band.out_row0 = pc.row0;
 	band.out_rows = pc.rows;
 	band.row_order = v.row_order;
-	band.shiftx = (job.op != OP_MEDIAN && job.seq->have_reg) ? d.shifts : nullptr;
-	band.shifty = (job.op != OP_MEDIAN && job.seq->have_reg) ? d.shifts + N : nullptr;
+	band.shiftx = pl.shifted ? d.shifts : nullptr;
+	band.shifty = pl.shifted ? d.shifts + pl.N : nullptr;
+}
+
+// upload the source rows of result rows [row0, row0 + rows) of one layer of every frame into the piece's band
+int upload_rows(const Plan &pl, Dev &d, const ssc_band &band, int layer, int row0, int rows, cudaStream_t st) {
+	const ssc_sequence_view &v = pl.job->seq->view;
+	int s0, sr;
+	source_rows(*pl.job, row0, rows, pl.H, s0, sr);
 	const cudaMemcpyKind kind = v.frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-	for (int f = 0; f < N; f++) {
-		const WORD *src = job.seq->frames[job.images[f]];
-		if (!src) return fail(SSC_ERR_GENERIC, "frame %d has no data", job.images[f]);
-		for (int c = 0; c < C; c++)
-			CU(cudaMemcpyAsync(d.frames + (size_t) f * band.frame_stride + (size_t) c * band.layer_stride,
-					src + ((size_t) c * H + buf_row0) * W, band.layer_stride * sizeof(WORD), kind, d.stream));
-		if ((f & 15) == 15 && !keep_running()) return fail(SSC_ERR_GENERIC, "cancelled");
+	WORD *dst = d.frames + (size_t) layer * band.layer_stride + (size_t) (s0 - band.buf_row0) * pl.W;
+	const size_t src_off = ((size_t) layer * pl.H + s0) * pl.W, bytes = (size_t) sr * pl.W * sizeof(WORD);
+	if (pl.strided) {	// equally spaced frames: one pitched copy for all of them
+		const WORD *src = pl.job->seq->frames[pl.job->images[0]] + src_off;
+		if (cudaMemcpy2DAsync(dst, band.frame_stride * sizeof(WORD), src, pl.host_stride, bytes, (size_t) pl.N, kind, st) != cudaSuccess)
+			return SSC_ERR_CUDA;
+		return SSC_OK;
+	}
+	for (int f = 0; f < pl.N; f++) {
+		const WORD *src = pl.job->seq->frames[pl.job->images[f]];
+		if (!src) return SSC_ERR_GENERIC;
+		if (cudaMemcpyAsync(dst + (size_t) f * band.frame_stride, src + src_off, bytes, kind, st) != cudaSuccess) return SSC_ERR_CUDA;
+	}
+	return SSC_OK;
+}
+
+// the band of one unit: a single layer, a row chunk
+void unit_band(const ssc_band &piece, const Unit &u, ssc_band &b) {
+	b = piece;
+	b.frames = piece.frames + (size_t) u.layer * piece.layer_stride;
+	b.layers = 1;
+	b.out_row0 = u.row0;
+	b.out_rows = u.rows;
+}
+
+#define DCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { d.err = std::string(#call) + ": " + cudaGetErrorString(e_); return SSC_ERR_CUDA; } } while (0)
+#define DRC(call, what) do { int r_ = (call); if (r_) { d.err = what; return r_; } } while (0)
+
+// K4 for one range of result rows of a piece (each storage row is counted exactly once: the rows themselves)
+int histogram_rows(const Plan &pl, Dev &d, const ssc_band &piece, int row0, int rows, bool layer0_only, cudaStream_t st) {
+	ssc_band hb = piece;
+	hb.out_row0 = piece.row_order == SSC_ROWS_SER ? pl.H - (row0 + rows) : row0;
+	hb.out_rows = rows;
+	return ssc::launch_histogram_ex(hb, d.group ? nullptr : d.hist, d.group ? ssc::peer_frame_hist(d.group) : nullptr, d.flags,
+			layer0_only, st);
+}
+
+// K5 + K6 once this device's counts are complete; the coefficients end up in d.coeff on every device
+int statistics_and_coefficients(const Plan &pl, Dev &d, cudaStream_t st) {
+	const Job &job = *pl.job;
+	if (d.group) {
+		DRC(ssc::peer_signal_histograms(d.group, st), "histogram signal failed");
+		DRC(ssc_dev_ikss_gather(d.group, pl.N, d.scratch, st), ssc_peer_last_error());
+		DRC(ssc_dev_norm_coeffs_gathered(d.group, pl.N, job.ref_pos, job.normalize, d.coeff, d.status, nullptr, st), ssc_peer_last_error());
+	} else {
+		DRC(ssc::launch_ikss(d.hist, pl.N, d.stats, d.scratch, st), "ikss launch failed");
+		DRC(ssc::launch_norm_coeffs(d.stats, pl.N, job.ref_pos, job.normalize, d.coeff, d.status, st), "norm_coeffs launch failed");
+	}
+	return SSC_OK;
+}
+
+// one unit through its kernel (everything but stack_summing's second pass)
+int launch_unit(const Plan &pl, Dev &d, const ssc_band &piece, const Piece &pc, const Unit &u, cudaStream_t st) {
+	const Job &job = *pl.job;
+	ssc_band ub;
+	unit_band(piece, u, ub);
+	const size_t layer_out = (size_t) pc.rows * pl.W;
+	if (job.op == OP_SUM)
+		return ssc::launch_sum_accumulate(ub, d.acc + (size_t) u.layer * layer_out + (size_t) (u.row0 - pc.row0) * pl.W, d.maxim, st);
+	if (job.op == OP_ADDMAX || job.op == OP_ADDMIN)
+		return ssc::launch_extreme(ub, job.op == OP_ADDMAX, d.out + (size_t) u.layer * layer_out + (size_t) (u.row0 - pc.row0) * pl.W,
+				reinterpret_cast<unsigned int *>(d.maxim), st);
+	ssc::StackParams p{};
+	p.band = ub;
+	p.normalize = job.normalize;
+	p.coeff = pl.need_norm ? d.coeff : nullptr;
+	p.rejection = job.rejection;
+	p.sig_low = job.sig[0];
+	p.sig_high = job.sig[1];
+	p.out = d.out + (size_t) u.layer * layer_out;
+	p.out_layer_stride = layer_out;
+	p.out_buf_row0 = pc.row0;
+	p.counters = d.counters + (size_t) u.layer * SSC_COUNTERS;	// the kernel sees layer 0: one counter set per layer
+	return ssc::launch_stack(p, job.op == OP_MEDIAN, st);
+}
+
+// download result rows [row0, row0 + rows) of a layer of a piece into the landing buffer
+int download_rows(const Plan &pl, Dev &d, const Piece &pc, int layer, int row0, int rows, cudaStream_t st) {
+	DCU(cudaMemcpyAsync(pl.landing + (size_t) layer * pl.plane + (size_t) row0 * pl.W,
+			d.out + ((size_t) layer * pc.rows + (row0 - pc.row0)) * pl.W, (size_t) rows * pl.W * sizeof(WORD),
+			cudaMemcpyDeviceToHost, st));
+	return SSC_OK;
+}
+
+void land(const Plan &pl, int layer, int row0, int rows) {	// pinned landing buffer -> the malloc()ed result
+	if (pl.landing == pl.result) return;
+	pl.result_ready.wait();
+	const size_t off = (size_t) layer * pl.plane + (size_t) row0 * pl.W;
+	memcpy(pl.result + off, pl.landing + off, (size_t) rows * pl.W * sizeof(WORD));
+}
+
+double ms_since(std::chrono::steady_clock::time_point t0) {
+	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---------------------------------------------------------------------------------------------
+// One device's share of the call, on its own host thread.  `phase` splits the work where the devices
+// have to meet on the host: 0 = everything up to stack_summing's maximum, 1 = the rest of stack_summing.
+//
+// Resident band (one piece): the frames go up chunk by chunk -- with normalization layer 0 of all
+// chunks first -- and everything else runs behind the copy front on other streams: K4 on every layer-0
+// chunk as it lands, K5 / K6 (with the NVLink exchange when several devices work), K3 / K2 on every unit
+// as soon as it is complete, its result rows down while the next unit is stacked.  The end-to-end time
+// is the upload plus one unit's kernel and download.
+// Several pieces (frames larger than the HBM budget): piece after piece, first all of them for the
+// statistics, then again for the stack.
+// ---------------------------------------------------------------------------------------------
+int device_run(const Plan &pl, Dev &d, int phase) {
+	const Job &job = *pl.job;
+	DevCache &dc = *d.dc;
+	DCU(cudaSetDevice(d.id));
+	const bool resident = d.pieces.size() == 1;
+	const auto t_begin = std::chrono::steady_clock::now();
+	size_t ev_next = 0;
+	auto new_event = [&](cudaEvent_t &e) -> int { return dc.event(ev_next++, e); };
+
+	if (job.op == OP_SUM && phase == 1) {	// K1b with the global maximum (already in d.maxim)
+		for (size_t k = 0; k < d.pieces.size(); k++) {
+			const Piece &pc = d.pieces[k];
+			ssc_band piece;
+			piece_band(pl, d, pc, piece);
+			if (!resident) {	// the accumulators of other pieces were overwritten: this piece's sums again
+				for (int c = 0; c < pl.C; c++) DRC(upload_rows(pl, d, piece, c, pc.row0, pc.rows, dc.comp), "upload failed");
+				for (const Unit &u : d.units)
+					if (u.piece == (int) k) DRC(ssc::launch_sum_accumulate([&] { ssc_band ub; unit_band(piece, u, ub); return ub; }(),
+							d.acc + ((size_t) u.layer * pc.rows + (u.row0 - pc.row0)) * pl.W, d.counters, dc.comp), "sum launch failed");
+			}
+			DRC(ssc::launch_sum_finish(d.acc, (size_t) pl.C * pc.rows * pl.W, d.maxim, d.out, dc.comp), "sum finish failed");
+			for (int c = 0; c < pl.C; c++) DRC(download_rows(pl, d, pc, c, pc.row0, pc.rows, dc.comp), "download failed");
+			DCU(cudaStreamSynchronize(dc.comp));
+			for (int c = 0; c < pl.C; c++) land(pl, c, pc.row0, pc.rows);
+		}
+		d.t_d2h += ms_since(t_begin);
+		return SSC_OK;
+	}
+
+	// ---- statistics over several pieces (or the statistics alone, ssc_compute_normalization): a pass of its own ----
+	const bool stats_only = d.units.empty();
+	if (pl.need_norm && (!resident || stats_only)) {
+		for (size_t k = 0; k < d.pieces.size(); k++) {
+			const Piece &pc = d.pieces[k];
+			ssc_band piece;
+			piece_band(pl, d, pc, piece);
+			const auto t0 = std::chrono::steady_clock::now();
+			for (int c = 0; c < pl.C; c++) DRC(upload_rows(pl, d, piece, c, pc.row0, pc.rows, dc.comp), "upload failed");
+			DCU(cudaStreamSynchronize(dc.comp));
+			d.t_h2d += ms_since(t0);
+			DRC(histogram_rows(pl, d, piece, pc.row0, pc.rows, false, dc.comp), "histogram launch failed");
+			DCU(cudaStreamSynchronize(dc.comp));	// the next piece overwrites the frames
+			if (*pl.cancel) return SSC_ERR_GENERIC;
+		}
+		DRC(statistics_and_coefficients(pl, d, dc.comp), d.err.c_str());
+		DCU(cudaStreamSynchronize(dc.comp));
+	}
+	if (stats_only) return SSC_OK;
+
+	// ---- the units ----
+	std::vector<cudaEvent_t> up(d.units.size()), done(d.units.size()), down(d.units.size());
+	for (size_t k = 0; k < d.pieces.size(); k++) {
+		const Piece &pc = d.pieces[k];
+		ssc_band piece;
+		piece_band(pl, d, pc, piece);
+		std::vector<size_t> mine;	// this piece's units, in upload order
+		for (size_t i = 0; i < d.units.size(); i++) if (d.units[i].piece == (int) k) mine.push_back(i);
+		if (resident && pl.need_norm)	// layer 0 first: the statistics only need that one
+			std::stable_sort(mine.begin(), mine.end(), [&](size_t a, size_t b) { return (d.units[a].layer != 0) < (d.units[b].layer != 0); });
+		const auto t_up = std::chrono::steady_clock::now();
+		for (size_t i : mine) {	// the copy stream runs ahead of everything else
+			const Unit &u = d.units[i];
+			DRC(upload_rows(pl, d, piece, u.layer, u.row0, u.rows, dc.copy), "upload failed");
+			DRC(new_event(up[i]), "event");
+			DCU(cudaEventRecord(up[i], dc.copy));
+		}
+		if (resident && pl.need_norm) {
+			// K4 behind the copy front, layer 0 chunk by chunk
+			for (size_t i : mine) {
+				const Unit &u = d.units[i];
+				if (u.layer != 0) continue;
+				DCU(cudaStreamWaitEvent(dc.comp, up[i], 0));
+				DRC(histogram_rows(pl, d, piece, u.row0, u.rows, true, dc.comp), "histogram launch failed");
+			}
+			if (pl.C > 1) {
+				// get_normalized_value (utils.c:454-459) looks at all layers, but only for a frame whose layer 0
+				// stays <= 255 in this band can the others matter: ask, and only then wait for the whole upload
+				std::vector<uint32_t> h_flags(pl.N);
+				DCU(cudaMemcpyAsync(h_flags.data(), d.flags, (size_t) pl.N * sizeof(uint32_t), cudaMemcpyDeviceToHost, dc.comp));
+				DCU(cudaStreamSynchronize(dc.comp));
+				bool all_set = true;
+				for (uint32_t f : h_flags) all_set = all_set && f != 0;
+				if (!all_set) {
+					DCU(cudaStreamWaitEvent(dc.comp, up[mine.back()], 0));
+					ssc_band hb = piece;
+					hb.out_row0 = piece.row_order == SSC_ROWS_SER ? pl.H - (pc.row0 + pc.rows) : pc.row0;
+					hb.out_rows = pc.rows;
+					DRC(ssc::launch_other_layers(hb, d.group ? nullptr : d.hist, d.group ? ssc::peer_frame_hist(d.group) : nullptr, d.flags, dc.comp),
+							"histogram launch failed");
+				}
+			}
+			DRC(statistics_and_coefficients(pl, d, dc.comp), d.err.c_str());
+		}
+		if (!resident) {	// (several pieces: the stack of this piece starts when its upload is complete)
+			DCU(cudaStreamSynchronize(dc.copy));
+			d.t_h2d += ms_since(t_up);
+		}
+		const bool streamed_out = job.op != OP_SUM;	// stack_summing writes after the global maximum is known
+		for (size_t i : mine) {
+			const Unit &u = d.units[i];
+			DCU(cudaStreamWaitEvent(dc.comp, up[i], 0));
+			DRC(launch_unit(pl, d, piece, pc, u, dc.comp), "stack launch failed");
+			if (streamed_out) {
+				DRC(new_event(done[i]), "event");
+				DCU(cudaEventRecord(done[i], dc.comp));
+				DCU(cudaStreamWaitEvent(dc.out, done[i], 0));
+				DRC(download_rows(pl, d, pc, u.layer, u.row0, u.rows, dc.out), "download failed");
+				DRC(new_event(down[i]), "event");
+				DCU(cudaEventRecord(down[i], dc.out));
+			}
+		}
+		if (resident) {
+			DCU(cudaStreamSynchronize(dc.copy));
+			d.t_h2d += ms_since(t_up);
+		}
+		const auto t_k = std::chrono::steady_clock::now();
+		if (streamed_out) {
+			for (size_t i : mine) {	// every unit's rows into the caller's image as they arrive
+				DCU(cudaEventSynchronize(down[i]));
+				land(pl, d.units[i].layer, d.units[i].row0, d.units[i].rows);
+			}
+		}
+		DCU(cudaStreamSynchronize(dc.comp));
+		d.t_dev += ms_since(t_k);	// what is left after the upload: the last unit's kernel and download
+		if (*pl.cancel) return SSC_ERR_GENERIC;
 	}
 	return SSC_OK;
 }
@@ -406,33 +675,52 @@ int run_job(const Job &job) {
 	std::vector<Dev> devs(G);
 	std::lock_guard<std::mutex> op_lock(g_op_mu);	// one operator call in flight (as in Siril: com.run_thread)
 
+	std::atomic<bool> cancel{false};
+	Plan pl{};
+	pl.job = &job;
+	pl.W = W; pl.H = H; pl.C = C; pl.N = N; pl.G = G;
+	pl.need_norm = need_norm;
+	pl.shifted = job.op != OP_MEDIAN && job.seq->have_reg;
+	pl.plane = plane;
+	pl.cancel = &cancel;
+	{	// equally spaced host frames (one big array, as a sequence read into memory usually is): pitched copies
+		pl.strided = N > 1;
+		const char *f0 = (const char *) job.seq->frames[job.images[0]], *f1 = N > 1 ? (const char *) job.seq->frames[job.images[1]] : f0;
+		if (!f0) return fail(SSC_ERR_GENERIC, "frame %d has no data", job.images[0]);
+		const ptrdiff_t st = f1 - f0;
+		for (int f = 0; f < N && pl.strided; f++) {
+			const char *p = (const char *) job.seq->frames[job.images[f]];
+			if (!p) return fail(SSC_ERR_GENERIC, "frame %d has no data", job.images[f]);
+			if (p - f0 != st * f) pl.strided = false;
+		}
+		if (st < (ptrdiff_t) (plane * C * sizeof(WORD))) pl.strided = false;
+		pl.host_stride = (size_t) st;
+	}
+
 	// --- plan: contiguous row bands per device (remainder rows to the first ones, as
 	// stacking.c:620-625 does), each split further if the frames do not fit in HBM ---
+	int reach = 0;
+	if (pl.shifted) {
+		int lo = 0, hi = 0;
+		for (int idx : job.images) { lo = std::min(lo, job.seq->sy[idx]); hi = std::max(hi, job.seq->sy[idx]); }
+		reach = hi - lo;
+	}
 	int row = 0;
 	for (int g = 0; g < G; g++) {
 		Dev &d = devs[g];
 		d.id = ids[g];
+		d.index = g;
 		const int rows = H / G + (g < H % G ? 1 : 0);
 		CU(cudaSetDevice(d.id));
 		size_t free_b = 0, total_b = 0;
-		mark("before cudaMemGetInfo");
 		CU(cudaMemGetInfo(&free_b, &total_b));
-		mark("after cudaMemGetInfo");
-		{
-			auto it = g_cache.find(d.id);	// what this library already holds on the device is reusable
-			if (it != g_cache.end()) free_b += it->second.frames.cap + it->second.out.cap + it->second.hist.cap
-					+ it->second.scratch.cap + it->second.acc.cap;
-		}
+		DevCache &dc = g_cache[d.id];
+		d.dc = &dc;
+		free_b += dc.frames.cap + dc.outb.cap + dc.hist.cap + dc.scratch.cap + dc.acc.cap;	// what this library already holds is reusable
 		// what the library itself keeps on the device besides frames and result: histograms and IKSS scratch,
 		// 4 bytes per result pixel for the hand-back lists of the register / warp kernels, and the extra
 		// source rows the y shifts reach for (source_rows())
 		size_t fixed = (size_t) N * (SSC_HIST_STRIDE + 65536) * 4 + (64u << 20);
-		int reach = 0;
-		if (job.op != OP_MEDIAN && job.seq->have_reg) {
-			int lo = 0, hi = 0;
-			for (int idx : job.images) { lo = std::min(lo, job.seq->sy[idx]); hi = std::max(hi, job.seq->sy[idx]); }
-			reach = hi - lo;
-		}
 		fixed += (size_t) reach * N * C * W * sizeof(WORD);
 		size_t budget = free_b > fixed ? (size_t) ((free_b - fixed) * 0.85) : 0;
 		if (const char *e = getenv("SSC_HBM_BUDGET_BYTES")) {	// tests force the row split with it
@@ -448,51 +736,69 @@ int run_job(const Job &job) {
 			d.pieces.push_back(Piece{row, r});
 			row += r;
 		}
-		d.resident = n_pieces == 1;
-		for (auto &pc : d.pieces) {
+		for (size_t k = 0; k < d.pieces.size(); k++) {
+			const Piece &pc = d.pieces[k];
 			int b0, br;
-			source_rows(job, pc, H, b0, br);
+			source_rows(job, pc.row0, pc.rows, H, b0, br);
 			d.max_rows = std::max(d.max_rows, pc.rows);
 			d.max_buf_rows = std::max(d.max_buf_rows, br);
+			// units: per layer; without registration shifts also in row chunks of ~64 MB of samples, so that the
+			// upload, the kernels and the download of consecutive chunks overlap
+			int chunk = pc.rows;
+			if (!pl.shifted && !v.frames_on_device) {
+				const size_t row_bytes = (size_t) N * W * sizeof(WORD);
+				size_t chunk_bytes = 64u << 20;
+				if (const char *e = getenv("SSC_CHUNK_BYTES")) {	// tests force many small chunks with it
+					const unsigned long long cb = strtoull(e, nullptr, 10);
+					if (cb > 0) chunk_bytes = (size_t) cb;
+				}
+				chunk = (int) std::max<size_t>(getenv("SSC_CHUNK_BYTES") ? 1 : 8, chunk_bytes / std::max<size_t>(row_bytes, 1));
+				const int n_chunks = std::min(64, std::max(1, (pc.rows + chunk - 1) / chunk));
+				chunk = (pc.rows + n_chunks - 1) / n_chunks;
+			}
+			for (int r0 = 0; r0 < pc.rows; r0 += chunk)	// chunk-major: a chunk's layers are consecutive
+				for (int c = 0; c < C; c++)
+					d.units.push_back(Unit{(int) k, c, pc.row0 + r0, std::min(chunk, pc.rows - r0)});
 		}
-		DevCache &dc = g_cache[d.id];
-		if (!dc.stream) CU(cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking));
-		d.stream = dc.stream;
+		for (cudaStream_t *s : {&dc.copy, &dc.comp, &dc.out})
+			if (!*s) CU(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
 #define SSC_ENSURE(buf, bytes) do { if (dc.buf.ensure(bytes)) return fail(SSC_ERR_CUDA, "device allocation of %zu bytes failed", (size_t) (bytes)); } while (0)
 		SSC_ENSURE(frames, (size_t) N * C * d.max_buf_rows * W * sizeof(WORD));
-		SSC_ENSURE(out, (size_t) C * d.max_rows * W * sizeof(WORD));
-		SSC_ENSURE(counters, SSC_COUNTERS * sizeof(unsigned long long));
+		SSC_ENSURE(outb, (size_t) C * d.max_rows * W * sizeof(WORD));
+		SSC_ENSURE(counters, (size_t) 3 * SSC_COUNTERS * sizeof(unsigned long long));
 		SSC_ENSURE(coeff, (size_t) 3 * N * sizeof(double));
-		d.frames = (WORD *) dc.frames.p; d.out = (WORD *) dc.out.p;
+		SSC_ENSURE(maxim, sizeof(unsigned long long));
+		d.frames = (WORD *) dc.frames.p; d.out = (WORD *) dc.outb.p;
 		d.counters = (unsigned long long *) dc.counters.p; d.coeff = (double *) dc.coeff.p;
-		CU(cudaMemsetAsync(d.counters, 0, SSC_COUNTERS * sizeof(unsigned long long), d.stream));
-		mark("buffers ensured");
+		d.maxim = (unsigned long long *) dc.maxim.p;
+		CU(cudaMemsetAsync(d.counters, 0, (size_t) 3 * SSC_COUNTERS * sizeof(unsigned long long), dc.comp));
+		{
+			const unsigned long long neutral = job.op == OP_ADDMIN ? 0xFFFFull : 0ull;	// low word = the extreme kernels' unsigned int
+			CU(cudaMemcpyAsync(d.maxim, &neutral, sizeof(neutral), cudaMemcpyHostToDevice, dc.comp));
+			CU(cudaStreamSynchronize(dc.comp));
+		}
 		if (job.op == OP_SUM) {
 			SSC_ENSURE(acc, (size_t) C * d.max_rows * W * sizeof(uint32_t));
-			SSC_ENSURE(maxim, sizeof(unsigned long long));
-			d.acc = (uint32_t *) dc.acc.p; d.maxim = (unsigned long long *) dc.maxim.p;
-			CU(cudaMemsetAsync(d.maxim, 0, sizeof(unsigned long long), d.stream));
-		}
-		if (job.op == OP_ADDMAX || job.op == OP_ADDMIN) {
-			SSC_ENSURE(maxim, sizeof(unsigned long long));
-			d.maxim = (unsigned long long *) dc.maxim.p;
-			const unsigned long long neutral = job.op == OP_ADDMAX ? 0ull : 0xFFFFull;	// low word = the kernel's unsigned int
-			CU(cudaMemcpyAsync(d.maxim, &neutral, sizeof(neutral), cudaMemcpyHostToDevice, d.stream));
-			CU(cudaStreamSynchronize(d.stream));
+			d.acc = (uint32_t *) dc.acc.p;
 		}
 		if (need_norm) {
-			SSC_ENSURE(hist, (size_t) N * SSC_HIST_STRIDE * sizeof(uint32_t));
-			d.hist = (uint32_t *) dc.hist.p;
-			CU(cudaMemsetAsync(d.hist, 0, (size_t) N * SSC_HIST_STRIDE * sizeof(uint32_t), d.stream));
-			if (g == 0) {
+			SSC_ENSURE(flags, (size_t) N * sizeof(uint32_t));
+			SSC_ENSURE(status, sizeof(int));
+			d.flags = (uint32_t *) dc.flags.p; d.status = (int *) dc.status.p;
+			CU(cudaMemsetAsync(d.flags, 0, (size_t) N * sizeof(uint32_t), dc.comp));
+			CU(cudaMemsetAsync(d.status, 0, sizeof(int), dc.comp));
+			if (G == 1) {
+				SSC_ENSURE(hist, (size_t) N * SSC_HIST_STRIDE * sizeof(uint32_t));
 				SSC_ENSURE(scratch, (size_t) N * 65536 * sizeof(uint32_t));
 				SSC_ENSURE(stats, (size_t) 4 * N * sizeof(double));
-				SSC_ENSURE(status, sizeof(int));
-				d.scratch = (uint32_t *) dc.scratch.p; d.stats = (double *) dc.stats.p; d.status = (int *) dc.status.p;
-				CU(cudaMemsetAsync(d.status, 0, sizeof(int), d.stream));
+				d.hist = (uint32_t *) dc.hist.p; d.scratch = (uint32_t *) dc.scratch.p; d.stats = (double *) dc.stats.p;
+				CU(cudaMemsetAsync(d.hist, 0, (size_t) N * SSC_HIST_STRIDE * sizeof(uint32_t), dc.comp));
+			} else {
+				SSC_ENSURE(scratch, (size_t) ((N + G - 1) / G) * 65536 * sizeof(uint32_t));
+				d.scratch = (uint32_t *) dc.scratch.p;
 			}
 		}
-		if (job.op != OP_MEDIAN && job.seq->have_reg) {
+		if (pl.shifted) {
 			std::vector<int> sh(2 * N);
 			for (int f = 0; f < N; f++) {
 				sh[f] = job.seq->sx[job.images[f]];
@@ -500,245 +806,152 @@ int run_job(const Job &job) {
 			}
 			SSC_ENSURE(shifts, 2 * N * sizeof(int));
 			d.shifts = (int *) dc.shifts.p;
-			CU(cudaMemcpyAsync(d.shifts, sh.data(), 2 * N * sizeof(int), cudaMemcpyHostToDevice, d.stream));
-			CU(cudaStreamSynchronize(d.stream));	// sh goes out of scope
+			CU(cudaMemcpyAsync(d.shifts, sh.data(), 2 * N * sizeof(int), cudaMemcpyHostToDevice, dc.comp));
+			CU(cudaStreamSynchronize(dc.comp));	// sh goes out of scope
 		}
 	}
+	// several devices: every device's end of the NVLink exchanges (kept between calls of the same shape)
+	if (G > 1) {
+		bool rebuild = false;
+		for (auto &d : devs) rebuild = rebuild || !d.dc->group || d.dc->group_ids != ids || d.dc->group_frames < N;
+		if (rebuild) {
+			for (auto &kv : g_cache)
+				if (kv.second.group) { cudaSetDevice(kv.first); ssc_peer_destroy(kv.second.group); kv.second.group = nullptr; }
+			for (auto &d : devs) {
+				CU(cudaSetDevice(d.id));
+				if (ssc_peer_create(G, d.index, N, &d.dc->group)) return fail(SSC_ERR_CUDA, "peer group: %s", ssc_peer_last_error());
+				d.dc->group_ids = ids;
+				d.dc->group_frames = N;
+			}
+			for (auto &d : devs) {
+				for (auto &o : devs)
+					if (ssc_peer_attach_local(d.dc->group, o.index, o.dc->group)) return fail(SSC_ERR_CUDA, "peer group: %s", ssc_peer_last_error());
+				if (ssc_peer_connect(d.dc->group)) return fail(SSC_ERR_CUDA, "peer group: %s", ssc_peer_last_error());
+			}
+		}
+		for (auto &d : devs) d.group = d.dc->group;
+	}
+	mark("planned, workspace ready");
 
 	// The result (malloc()ed: it becomes gfit.data, stacking.c:776-785) is allocated now and its pages
 	// are touched on a helper thread while the frames upload: first-touch faults on 100+ MB would
 	// otherwise sit between the download and the caller.
 	WORD *result = job.want_coeff_only ? nullptr : (WORD *) malloc(plane * C * sizeof(WORD));
 	struct ResultGuard { WORD *&p; ~ResultGuard() { free(p); } } rguard{result};
-	struct Prefault {
-		std::thread th;
-		void join() { if (th.joinable()) th.join(); }
-		~Prefault() { join(); }
-	} prefault;
+	if (!job.want_coeff_only && !result) return fail(SSC_ERR_GENERIC, "result allocation failed");
 	if (result) {
 		WORD *r = result;
 		const size_t bytes = plane * C * sizeof(WORD);
-		prefault.th = std::thread([r, bytes] { memset(r, 0, bytes); });
-	}
-	mark("planned, workspace ready");
-	double t_h2d = 0, t_dev = 0, t_d2h = 0;
-	auto t_phase = clk::now();
-	auto phase_end = [&](double &acc_ms) -> int {	// sync all devices, book the wall time of this phase
-		for (auto &d : devs) {
-			CU(cudaSetDevice(d.id));
-			CU(cudaStreamSynchronize(d.stream));
+		pl.result_ready = std::async(std::launch::async, [r, bytes] { memset(r, 0, bytes); }).share();
+		// device -> pinned bounce buffer (full PCIe speed), then into the malloc()ed result
+		if (g_pinned_cap < bytes) {
+			if (g_pinned) cudaFreeHost(g_pinned);
+			g_pinned = nullptr; g_pinned_cap = 0;
+			if (cudaHostAlloc(&g_pinned, bytes, cudaHostAllocPortable) == cudaSuccess) g_pinned_cap = bytes;
 		}
-		auto now = clk::now();
-		acc_ms += std::chrono::duration<double, std::milli>(now - t_phase).count();
-		t_phase = now;
-		return SSC_OK;
-	};
-	{
-		int rc = phase_end(t_dev);	// allocation / setup is booked as device time
-		if (rc) return rc;
 	}
-
-	std::vector<ssc_band> bands(G);
-	int rc;
-	mark("setup synchronised");
-
-	// --- normalization statistics: K4 per band, combine, K5, K6 ---
+	struct ReadyGuard { std::shared_future<void> &f; ~ReadyGuard() { if (f.valid()) f.wait(); } } ready_guard{pl.result_ready};
+	pl.result = result;
+	pl.landing = g_pinned ? (WORD *) g_pinned : result;
 	std::vector<double> h_coeff((size_t) 3 * N);
+	for (int i = 0; i < N; i++) { h_coeff[i] = 0.0; h_coeff[N + i] = 1.0; h_coeff[2 * N + i] = 1.0; }
+
 	if (need_norm) {
 		log_msg("Computing normalization...\n");
 		progress("Computing normalization...", 0.0);
-		size_t max_pieces = 0;
-		for (auto &d : devs) max_pieces = std::max(max_pieces, d.pieces.size());
-		for (size_t k = 0; k < max_pieces; k++) {
-			for (int g = 0; g < G; g++) {
-				Dev &d = devs[g];
-				if (k >= d.pieces.size()) continue;
-				CU(cudaSetDevice(d.id));
-				if ((rc = upload_piece(job, d, d.pieces[k], bands[g]))) return rc;
-			}
-			if ((rc = phase_end(t_h2d))) return rc;
-			for (int g = 0; g < G; g++) {
-				Dev &d = devs[g];
-				if (k >= d.pieces.size()) continue;
-				CU(cudaSetDevice(d.id));
-				ssc_band hb = bands[g];
-				// histogram each storage row exactly once: the piece's own rows
-				hb.out_row0 = v.row_order == SSC_ROWS_SER ? H - (d.pieces[k].row0 + d.pieces[k].rows) : d.pieces[k].row0;
-				hb.out_rows = d.pieces[k].rows;
-				if ((rc = ssc::launch_histogram(hb, d.hist, d.stream))) return fail(rc, "histogram launch failed");
-			}
-			if ((rc = phase_end(t_dev))) return rc;
+	}
+	if (job.want_coeff_only)	// ssc_compute_normalization: K4 over every piece, K5, K6 -- no unit is ever launched
+		for (auto &d : devs) d.units.clear();
+
+	// --- every device on its own host thread; the caller's cancel hook is polled here, on the calling thread ---
+	auto run_phase = [&](int phase) -> int {
+		std::atomic<int> running{G};
+		std::vector<std::thread> th;
+		for (int g = 0; g < G; g++)
+			th.emplace_back([&, g] {
+				devs[g].rc = device_run(pl, devs[g], phase);
+				running--;
+			});
+		while (running.load() > 0) {
+			std::this_thread::sleep_for(std::chrono::milliseconds(2));
+			if (!keep_running()) cancel = true;	// the device threads stop at their next piece
 		}
-		// combine on device 0 (exact integer sums), then K5 + K6 there, broadcast the coefficients
+		for (auto &t : th) t.join();
+		int bad = SSC_OK;
+		for (auto &d : devs)
+			if (d.rc && !bad) bad = fail(d.rc, "device %d: %s", d.id, d.err.empty() ? (cancel ? "cancelled" : "failed") : d.err.c_str());
+		if (bad)	// the devices' exchange epochs may have drifted apart: new peer groups next time
+			for (auto &d : devs)
+				if (d.dc->group) { cudaSetDevice(d.id); cudaDeviceSynchronize(); ssc_peer_destroy(d.dc->group); d.dc->group = nullptr; }
+		return bad;
+	};
+	if (!job.want_coeff_only) log_msg("Starting stacking...\n");
+	int rc = run_phase(0);
+	if (rc) return rc;
+	mark("phase 0 done");
+
+	if (need_norm) {
 		Dev &d0 = devs[0];
-		CU(cudaSetDevice(d0.id));
-		if (G > 1) {
-			std::vector<uint32_t> h_sum((size_t) N * SSC_HIST_STRIDE), h_tmp((size_t) N * SSC_HIST_STRIDE);
-			CU(cudaMemcpy(h_sum.data(), d0.hist, h_sum.size() * 4, cudaMemcpyDeviceToHost));
-			for (int g = 1; g < G; g++) {
-				CU(cudaSetDevice(devs[g].id));
-				CU(cudaMemcpy(h_tmp.data(), devs[g].hist, h_tmp.size() * 4, cudaMemcpyDeviceToHost));
-				for (size_t i = 0; i < h_sum.size(); i++) h_sum[i] += h_tmp[i];
-			}
-			CU(cudaSetDevice(d0.id));
-			CU(cudaMemcpy(d0.hist, h_sum.data(), h_sum.size() * 4, cudaMemcpyHostToDevice));
-		}
-		if ((rc = ssc::launch_ikss(d0.hist, N, d0.stats, d0.scratch, d0.stream))) return fail(rc, "ikss launch failed");
-		if ((rc = ssc::launch_norm_coeffs(d0.stats, N, job.ref_pos, job.normalize, d0.coeff, d0.status, d0.stream)))
-			return fail(rc, "norm_coeffs launch failed");
 		int h_status = 0;
-		CU(cudaMemcpyAsync(h_coeff.data(), d0.coeff, h_coeff.size() * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
-		CU(cudaMemcpyAsync(&h_status, d0.status, sizeof(int), cudaMemcpyDeviceToHost, d0.stream));
-		CU(cudaStreamSynchronize(d0.stream));
+		CU(cudaSetDevice(d0.id));
+		CU(cudaMemcpy(h_coeff.data(), d0.coeff, h_coeff.size() * sizeof(double), cudaMemcpyDeviceToHost));
+		for (auto &d : devs) {
+			int s = 0;
+			CU(cudaSetDevice(d.id));
+			CU(cudaMemcpy(&s, d.status, sizeof(int), cudaMemcpyDeviceToHost));
+			h_status |= s;
+			if (d.group && ssc_peer_status(d.group, d.dc->comp)) return fail(SSC_ERR_CUDA, "device %d waited for a peer that never arrived", d.id);
+		}
 		if (h_status) {
 			log_msg("Error: no data computed.\n");
 			return fail(SSC_ERR_GENERIC, "a frame has no non-zero pixel: no statistics");
 		}
-		for (int g = 1; g < G; g++) {
-			CU(cudaSetDevice(devs[g].id));
-			CU(cudaMemcpyAsync(devs[g].coeff, h_coeff.data(), h_coeff.size() * sizeof(double), cudaMemcpyHostToDevice, devs[g].stream));
-		}
-		if ((rc = phase_end(t_dev))) return rc;
 		progress(nullptr, 1.0);
-	} else {
-		for (int i = 0; i < N; i++) { h_coeff[i] = 0.0; h_coeff[N + i] = 1.0; h_coeff[2 * N + i] = 1.0; }
 	}
 	if (job.coeff_out) memcpy(job.coeff_out, h_coeff.data(), h_coeff.size() * sizeof(double));
 	if (job.want_coeff_only) return SSC_OK;
 	if (!keep_running()) return fail(SSC_ERR_GENERIC, "cancelled");
 
-	// --- the stack itself ---
-	if (!result) return fail(SSC_ERR_GENERIC, "result allocation failed");
-
-	mark("normalization done");
-	log_msg("Starting stacking...\n");
 	unsigned long long h_max = 0;
-	size_t max_pieces = 0;
-	for (auto &d : devs) max_pieces = std::max(max_pieces, d.pieces.size());
-	const int sum_passes = job.op == OP_SUM ? 2 : 1;	// sum: all pieces accumulate the max before any is scaled
-	for (int pass = 0; pass < sum_passes; pass++) {
-		for (size_t k = 0; k < max_pieces; k++) {
-			bool uploaded = false;
-			for (int g = 0; g < G; g++) {
-				Dev &d = devs[g];
-				if (k >= d.pieces.size()) continue;
-				CU(cudaSetDevice(d.id));
-				const bool have = d.resident && (need_norm || pass > 0);
-				if (!have) {
-					if ((rc = upload_piece(job, d, d.pieces[k], bands[g]))) return rc;
-					uploaded = true;
-				}
-			}
-			if (uploaded && (rc = phase_end(t_h2d))) return rc;
-			for (int g = 0; g < G; g++) {
-				Dev &d = devs[g];
-				if (k >= d.pieces.size()) continue;
-				CU(cudaSetDevice(d.id));
-				const Piece &pc = d.pieces[k];
-				ssc::StackParams p{};
-				p.band = bands[g];
-				p.normalize = job.normalize;
-				p.coeff = need_norm ? d.coeff : nullptr;
-				p.rejection = job.rejection;
-				p.sig_low = job.sig[0];
-				p.sig_high = job.sig[1];
-				p.out = d.out;
-				p.out_layer_stride = (size_t) pc.rows * W;
-				p.out_buf_row0 = pc.row0;
-				p.counters = d.counters;
-				if (job.op == OP_SUM) {
-					if (pass == 0) {
-						if ((rc = ssc::launch_sum_accumulate(bands[g], d.acc, d.maxim, d.stream))) return fail(rc, "sum launch failed");
-					} else {
-						if (!d.resident || max_pieces > 1) {
-							// accumulators of other pieces were overwritten: recompute this piece's sums
-							unsigned long long *scratch_max = d.counters;	// discard: the global max is already known
-							if ((rc = ssc::launch_sum_accumulate(bands[g], d.acc, scratch_max, d.stream))) return fail(rc, "sum launch failed");
-						}
-						if ((rc = ssc::launch_sum_finish(d.acc, (size_t) C * pc.rows * W, d.maxim, d.out, d.stream))) return fail(rc, "sum finish failed");
-					}
-				} else if (job.op == OP_ADDMAX || job.op == OP_ADDMIN) {
-					if ((rc = ssc::launch_extreme(bands[g], job.op == OP_ADDMAX, d.out, reinterpret_cast<unsigned int *>(d.maxim), d.stream)))
-						return fail(rc, "addmax/addmin launch failed");
-				} else {
-					if ((rc = ssc::launch_stack(p, job.op == OP_MEDIAN, d.stream)))
-						return fail(rc, "stack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-				}
-			}
-			if ((rc = phase_end(t_dev))) return rc;
-			if (job.op != OP_SUM || pass == 1) {
-				// device -> pinned bounce buffer (full PCIe speed), then into the malloc()ed result
-				if (g_pinned_cap < plane * C * sizeof(WORD)) {
-					if (g_pinned) cudaFreeHost(g_pinned);
-					g_pinned = nullptr; g_pinned_cap = 0;
-					if (cudaHostAlloc(&g_pinned, plane * C * sizeof(WORD), cudaHostAllocDefault) == cudaSuccess)
-						g_pinned_cap = plane * C * sizeof(WORD);
-				}
-				WORD *landing = g_pinned ? (WORD *) g_pinned : result;
-				prefault.join();	// (long done: the upload took far longer than touching the pages)
-				for (int g = 0; g < G; g++) {
-					Dev &d = devs[g];
-					if (k >= d.pieces.size()) continue;
-					CU(cudaSetDevice(d.id));
-					const Piece &pc = d.pieces[k];
-					for (int c = 0; c < C; c++)
-						CU(cudaMemcpyAsync(landing + (size_t) c * plane + (size_t) pc.row0 * W,
-								d.out + (size_t) c * pc.rows * W, (size_t) pc.rows * W * sizeof(WORD),
-								cudaMemcpyDeviceToHost, d.stream));
-				}
-				for (auto &d : devs) {
-					CU(cudaSetDevice(d.id));
-					CU(cudaStreamSynchronize(d.stream));
-				}
-				if (landing != result) {
-					std::vector<std::thread> th;
-					for (int g = 0; g < G; g++) {
-						Dev &d = devs[g];
-						if (k >= d.pieces.size()) continue;
-						const Piece pc = d.pieces[k];
-						for (int c = 0; c < C; c++) {
-							const size_t off = (size_t) c * plane + (size_t) pc.row0 * W, cnt = (size_t) pc.rows * W;
-							const int parts = 4;
-							for (int q = 0; q < parts; q++) {
-								const size_t a = cnt * q / parts, z = cnt * (q + 1) / parts;
-								th.emplace_back([=] { memcpy(result + off + a, landing + off + a, (z - a) * sizeof(WORD)); });
-							}
-						}
-					}
-					for (auto &t : th) t.join();
-				}
-				if ((rc = phase_end(t_d2h))) return rc;
-			}
-			progress(nullptr, (double) (k + 1) / (double) max_pieces);
-			if (!keep_running()) return fail(SSC_ERR_GENERIC, "cancelled");
+	if (job.op == OP_SUM) {
+		// the only exchange of this operator: the global max (stacking.c:311-313,328-330)
+		for (auto &d : devs) {
+			unsigned long long m = 0;
+			CU(cudaSetDevice(d.id));
+			CU(cudaMemcpy(&m, d.maxim, sizeof(m), cudaMemcpyDeviceToHost));
+			h_max = std::max(h_max, m);
 		}
-		if (job.op == OP_SUM && pass == 0) {
-			// the only exchange of this operator: the global max (stacking.c:311-313,328-330)
-			for (auto &d : devs) {
-				unsigned long long m = 0;
-				CU(cudaSetDevice(d.id));
-				CU(cudaMemcpy(&m, d.maxim, sizeof(m), cudaMemcpyDeviceToHost));
-				h_max = std::max(h_max, m);
-			}
-			for (auto &d : devs) {
-				CU(cudaSetDevice(d.id));
-				CU(cudaMemcpy(d.maxim, &h_max, sizeof(h_max), cudaMemcpyHostToDevice));
-			}
+		for (auto &d : devs) {
+			CU(cudaSetDevice(d.id));
+			CU(cudaMemcpy(d.maxim, &h_max, sizeof(h_max), cudaMemcpyHostToDevice));
 		}
+		if ((rc = run_phase(1))) return rc;
 	}
+	{
+		size_t max_pieces = 0;
+		for (auto &d : devs) max_pieces = std::max(max_pieces, d.pieces.size());
+		for (size_t k = 0; k < max_pieces; k++) progress(nullptr, (double) (k + 1) / (double) max_pieces);
+	}
+	if (!keep_running()) return fail(SSC_ERR_GENERIC, "cancelled");
 
 	mark("stack + download done");
 	ssc_result res;
 	memset(&res, 0, sizeof(res));
 	for (auto &d : devs) {
-		unsigned long long h_cnt[SSC_COUNTERS];
+		unsigned long long h_cnt[3 * SSC_COUNTERS];
 		CU(cudaSetDevice(d.id));
 		CU(cudaMemcpy(h_cnt, d.counters, sizeof(h_cnt), cudaMemcpyDeviceToHost));
 		if (job.op == OP_MEAN) {
-			for (int i = 0; i < 6; i++) res.irej[i / 2][i % 2] += h_cnt[i];
-			res.guard_fired += h_cnt[6];
-			res.cap_hit += h_cnt[7];
+			for (int c = 0; c < C; c++) {	// one counter set per layer (every unit's kernel saw a single layer)
+				res.irej[c][0] += h_cnt[c * SSC_COUNTERS + 0];
+				res.irej[c][1] += h_cnt[c * SSC_COUNTERS + 1];
+				res.guard_fired += h_cnt[c * SSC_COUNTERS + 6];
+				res.cap_hit += h_cnt[c * SSC_COUNTERS + 7];
+			}
 		}
+		res.t_h2d_ms = std::max(res.t_h2d_ms, d.t_h2d);
+		res.t_device_ms = std::max(res.t_device_ms, d.t_dev);
+		res.t_d2h_ms = std::max(res.t_d2h_ms, d.t_d2h);
 	}
 	res.data = result;
 	result = nullptr;	// ownership moves to the result
@@ -761,9 +974,6 @@ int run_job(const Job &job) {
 		}
 		res.hi = (WORD) e;
 	}
-	res.t_h2d_ms = t_h2d;
-	res.t_device_ms = t_dev;
-	res.t_d2h_ms = t_d2h;
 	res.t_total_ms = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count();
 
 	if (job.op == OP_MEAN) {

@@ -57,6 +57,16 @@ int launch_sum_finish(const uint32_t *acc, size_t count, const unsigned long lon
 
 // ssc_stats.cu
 int launch_histogram(const ssc_band &b, uint32_t *hist, cudaStream_t stream);
+// the same with one histogram pointer per frame (device array; may point into peer GPUs' memory)
+int launch_histogram_to(const ssc_band &b, uint32_t *hist, uint32_t *const *frame_hist, cudaStream_t stream);
+int launch_histogram_ex(const ssc_band &b, uint32_t *hist, uint32_t *const *frame_hist, uint32_t *local_gt255,
+		bool layer0_only, cudaStream_t stream);
+int launch_other_layers(const ssc_band &b, uint32_t *hist, uint32_t *const *frame_hist, const uint32_t *local_gt255,
+		cudaStream_t stream);
+
+// ssc_peer.cu, for the operator layer: the pieces of the exchanges it sequences itself
+uint32_t *const *peer_frame_hist(ssc_peer_group *g);	// device array: histogram pointer of every frame (at its owner)
+int peer_signal_histograms(ssc_peer_group *g, cudaStream_t stream);	// "this rank's counts are all in"
 int launch_ikss(const uint32_t *hist, int n_frames, double *stats, uint32_t *scratch, cudaStream_t stream);
 int launch_norm_coeffs(const double *stats, int n_frames, int ref_image, int mode, double *coeff,
 		int *status, cudaStream_t stream);

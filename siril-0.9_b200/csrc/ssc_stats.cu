@@ -36,7 +36,8 @@ constexpr unsigned int HIST_GROUP_SAMPLES = HIST_DEPTH * HIST_THREADS * 8;	// 24
 constexpr size_t HIST_SMEM = (32768 + HIST_WIN) * sizeof(uint32_t);
 
 __global__ void __launch_bounds__(HIST_THREADS, 1)
-k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
+k_histogram(ssc_band b, uint32_t *__restrict__ hist, uint32_t *const *__restrict__ frame_hist,
+		uint32_t *__restrict__ local_gt255, int ctas_per_frame) {
 	extern __shared__ __align__(16) uint32_t sh[];	// full[32768], then win[HIST_WIN]
 	__shared__ unsigned int any_gt255, s_base, s_outside[2], s_acc[32];
 	const int frame = blockIdx.x / ctas_per_frame;
@@ -44,7 +45,9 @@ k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
 	const int tid = threadIdx.x, lane = tid & 31;
 	const size_t band_px = (size_t) b.out_rows * b.width;	// layer-0 samples of this band
 	const WORD *src = b.frames + (size_t) frame * b.frame_stride + (size_t) (b.out_row0 - b.buf_row0) * b.width;
-	uint32_t *gh = hist + (size_t) frame * SSC_HIST_STRIDE;
+	// frame_hist: one histogram pointer per frame instead of a dense array -- with several GPUs every frame's
+	// histogram lives on the GPU that analyses it and the flushes below add into it over NVLink (ssc_peer.cu)
+	uint32_t *gh = frame_hist ? frame_hist[frame] : hist + (size_t) frame * SSC_HIST_STRIDE;
 
 	for (int i = tid; i < 32768 + HIST_WIN; i += HIST_THREADS) sh[i] = 0;
 	if (tid == 0) { any_gt255 = 0; s_outside[0] = s_outside[1] = 0; }
@@ -179,16 +182,20 @@ k_histogram(ssc_band b, uint32_t *__restrict__ hist, int ctas_per_frame) {
 	// word 65537: "layer 0 of this band has a sample > 255" (consumed by k_other_layers_gt255)
 	if ((seen & 0xFFFFu) > 255u || (seen >> 16) > 255u) atomicOr(&any_gt255, 1u);	// (seen collects packed pairs and single samples)
 	__syncthreads();
-	if (tid == 0 && any_gt255) atomicOr(&gh[65537], 1u);
+	if (tid == 0 && any_gt255) {
+		atomicOr(&gh[65537], 1u);
+		if (local_gt255) local_gt255[frame] = 1u;	// the same fact kept on this GPU (gh may be a peer's memory)
+	}
 }
 
 // get_normalized_value (src/core/utils.c:454-459) looks at the max over ALL
 // layers.  Only when layer 0 of this band stays <= 255 can the other layers
 // matter; then count their samples > 255 into word 65536.
-__global__ void k_other_layers_gt255(ssc_band b, uint32_t *__restrict__ hist) {
+__global__ void k_other_layers_gt255(ssc_band b, uint32_t *__restrict__ hist, uint32_t *const *__restrict__ frame_hist,
+		const uint32_t *__restrict__ local_gt255) {
 	const int frame = blockIdx.y;
-	uint32_t *gh = hist + (size_t) frame * SSC_HIST_STRIDE;
-	if (gh[65537] != 0) return;
+	uint32_t *gh = frame_hist ? frame_hist[frame] : hist + (size_t) frame * SSC_HIST_STRIDE;
+	if (local_gt255 ? local_gt255[frame] != 0 : gh[65537] != 0) return;
 	const size_t band_px = (size_t) b.out_rows * b.width;
 	unsigned int cnt = 0;
 	for (int layer = 1; layer < b.layers; layer++) {
@@ -203,7 +210,27 @@ __global__ void k_other_layers_gt255(ssc_band b, uint32_t *__restrict__ hist) {
 }
 
 int launch_histogram(const ssc_band &b, uint32_t *hist, cudaStream_t stream) {
-	if (b.n_frames < 1) return SSC_ERR_ARG;
+	return launch_histogram_to(b, hist, nullptr, stream);
+}
+
+int launch_histogram_to(const ssc_band &b, uint32_t *hist, uint32_t *const *frame_hist, cudaStream_t stream) {
+	return launch_histogram_ex(b, hist, frame_hist, nullptr, false, stream);
+}
+
+// the second half of K4 on its own: samples > 255 in layers 1.. of the frames whose layer 0 stayed <= 255
+int launch_other_layers(const ssc_band &b, uint32_t *hist, uint32_t *const *frame_hist, const uint32_t *local_gt255,
+		cudaStream_t stream) {
+	if (b.layers < 2) return SSC_OK;
+	dim3 grid(8, b.n_frames);
+	k_other_layers_gt255<<<grid, 256, 0, stream>>>(b, hist, frame_hist, local_gt255);
+	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
+}
+
+// local_gt255 (device uint32_t [n_frames], may be NULL): set to 1 for frames whose layer 0 has a sample > 255 in
+// this band; layer0_only: leave the other layers to a later launch_other_layers (they may not be uploaded yet)
+int launch_histogram_ex(const ssc_band &b, uint32_t *hist, uint32_t *const *frame_hist, uint32_t *local_gt255,
+		bool layer0_only, cudaStream_t stream) {
+	if (b.n_frames < 1 || (!hist && !frame_hist)) return SSC_ERR_ARG;
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -229,13 +256,9 @@ int launch_histogram(const ssc_band &b, uint32_t *hist, cudaStream_t stream) {
 	}
 	if ((size_t) per_frame > max_parts) per_frame = (int) max_parts;
 	if (per_frame < 1) per_frame = 1;
-	k_histogram<<<b.n_frames * per_frame, HIST_THREADS, HIST_SMEM, stream>>>(b, hist, per_frame);
+	k_histogram<<<b.n_frames * per_frame, HIST_THREADS, HIST_SMEM, stream>>>(b, hist, frame_hist, local_gt255, per_frame);
 	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
-	if (b.layers > 1) {
-		dim3 grid(8, b.n_frames);
-		k_other_layers_gt255<<<grid, 256, 0, stream>>>(b, hist);
-		if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
-	}
+	if (b.layers > 1 && !layer0_only) return launch_other_layers(b, hist, frame_hist, local_gt255, stream);
 	return SSC_OK;
 }
 

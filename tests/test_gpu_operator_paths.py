@@ -162,3 +162,113 @@ def test_several_devices_in_one_operator_call(gpu, port, ndev):
         assert np.array_equal(many[0].data, same["out"])
     finally:
         gpu.set_devices([0])
+
+
+@pytest.mark.skipif("not multi()", reason="needs two CUDA devices (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("n", [5, 16])
+def test_peer_group_exchange_in_one_process(gpu, port, n):
+    """ssc_peer_*: the NVLink exchanges of the device layer driven from one process (ssc_peer_attach_local).
+    Every device holds a row band; K4 adds its counts into the owners' histograms, K5 runs on the owned
+    frames, the statistics are stored into every device's table, K6 follows: coefficients, image and
+    counters equal the single-device pipeline bit for bit -- also on a second call (epochs), with a frame
+    count that does not divide by the device count, and for stack_summing's maximum."""
+    import torch
+    from test_gpu_device_layer import dev_u16, host_u16, run_pipeline
+    ndev = min(gpu.device_count(), 4)
+    c, h, w = 3, 41, 48
+    fr = synth.make_frames(n, c, h, w, seed=40 + n, outlier_p=5e-3, zero_p=1e-3, stars=3)
+    torch.cuda.set_device(0)
+    ref_out, ref_cnt, ref_coeff = run_pipeline(gpu, dev_u16(fr), n, c, h, w, [(0, h)], 2, (4.0, 3.0), 3)
+    groups = []
+    for g in range(ndev):
+        torch.cuda.set_device(g)
+        groups.append(gpu.PeerGroup(ndev, g, n))
+    for g in range(ndev):
+        torch.cuda.set_device(g)
+        for o in range(ndev):
+            groups[g].attach_local(o, groups[o])
+        groups[g].connect()
+    rows = [(g * h // ndev, (g + 1) * h // ndev - g * h // ndev) for g in range(ndev)]
+    bufs = []
+    for g in range(ndev):
+        torch.cuda.set_device(g)
+        dv = torch.device("cuda", g)
+        bufs.append(dict(frames=torch.from_numpy(fr.view(np.int16)).to(dv), out=torch.zeros((c, h, w), dtype=torch.int16, device=dv),
+                         scratch=torch.empty(((n + ndev - 1) // ndev, 65536), dtype=torch.int32, device=dv),
+                         coeff=torch.empty((3, n), dtype=torch.float64, device=dv), status=torch.zeros(1, dtype=torch.int32, device=dv),
+                         cnt=torch.zeros(8, dtype=torch.int64, device=dv), tot=torch.zeros(8, dtype=torch.int64, device=dv),
+                         mx=torch.zeros(1, dtype=torch.int64, device=dv)))
+    try:
+        for call in range(2):
+            for stage in range(4):                      # every stage on all devices before the next: nothing may block the host
+                for g in range(ndev):
+                    torch.cuda.set_device(g)
+                    b, sp = bufs[g], torch.cuda.current_stream().cuda_stream
+                    r0, rn = rows[g]
+                    band = gpu.dev.band(b["frames"].data_ptr(), n, c, h, w, out_row0=r0, out_rows=rn)
+                    if stage == 0:
+                        b["cnt"].zero_()
+                        groups[g].histogram_scatter(band, True, sp)
+                    elif stage == 1:
+                        groups[g].ikss_gather(n, b["scratch"].data_ptr(), sp)
+                    elif stage == 2:
+                        groups[g].norm_coeffs_gathered(n, 0, 3, b["coeff"].data_ptr(), b["status"].data_ptr(), None, sp)
+                        gpu.dev.stack_mean(band, b["out"].data_ptr(), b["cnt"].data_ptr(), 2, (4.0, 3.0), 3, b["coeff"].data_ptr(),
+                                           out_layer_stride=h * w, out_buf_row0=0, stream=sp)
+                    else:
+                        groups[g].counters_combine(b["cnt"].data_ptr(), b["tot"].data_ptr(), sp)
+                        b["mx"].fill_(1000 * (g + 1) + call)
+                        groups[g].max_combine(b["mx"].data_ptr(), sp)
+            out = np.zeros((c, h, w), np.uint16)
+            for g in range(ndev):
+                torch.cuda.set_device(g)
+                torch.cuda.synchronize()
+                assert groups[g].status() == 0
+                r0, rn = rows[g]
+                out[:, r0:r0 + rn] = host_u16(bufs[g]["out"])[:, r0:r0 + rn]
+                assert np.array_equal(bufs[g]["coeff"].cpu().numpy(), ref_coeff)         # exact under sharding
+                assert np.array_equal(bufs[g]["tot"].cpu().numpy(), ref_cnt)             # the same totals everywhere
+                assert int(bufs[g]["mx"].item()) == 1000 * ndev + call
+            assert np.array_equal(out, ref_out)
+    finally:
+        for g in range(ndev):
+            torch.cuda.set_device(g)
+            groups[g].close()
+        torch.cuda.set_device(0)
+
+
+@pytest.mark.parametrize("row_order", [0, 1])
+def test_chunked_pipeline_equals_one_chunk(gpu, port, row_order, monkeypatch):
+    """The operators upload, stack and download a resident band in row chunks per layer (layer 0 first when
+    statistics are needed: K4 runs behind the copy front).  SSC_CHUNK_BYTES forces many small chunks: every
+    operator must return what it returns in one chunk, and what the oracle says -- also for frames that
+    are not equally spaced in host memory (per-frame copies instead of one pitched copy) and for an 8-bit
+    sequence whose other layers decide the histogram range (utils.c:454-459)."""
+    n, c, h, w = 10, 3, 37, 40
+    fr = synth.make_frames(n, c, h, w, seed=77, outlier_p=5e-3, zero_p=1e-3, stars=3)
+    rnd = synth.make_random(n, c, h, w, seed=6, hi=9000)
+    scattered = [fr[i].copy() for i in (3, 0, 7, 1, 9, 2, 8, 4, 6, 5)]          # separate allocations, shuffled
+    small = synth.make_random(4, 3, 16, 32, seed=1, lo=0, hi=200)
+    small[1, 2, 3, 3] = 300                                                    # another layer lifts one frame's max
+    def run_all():
+        s, r = gpu.Sequence(fr, row_order=row_order), gpu.Sequence(rnd, row_order=row_order)
+        return [gpu.stack_mean_with_rejection(s, 2, (4.0, 3.0), 2), gpu.stack_mean_with_rejection(s, 4, (4.0, 3.0), 3),
+                gpu.stack_mean_with_rejection(s, 5, (5.0, 2.5), 0), gpu.stack_median(s, normalize=1, want_coeff=True),
+                gpu.stack_summing(r), gpu.stack_addmax(r), gpu.stack_addmin(r),
+                gpu.stack_mean_with_rejection(gpu.Sequence(scattered, row_order=row_order), 2, (4.0, 3.0), 4),
+                gpu.stack_mean_with_rejection(gpu.Sequence(small, row_order=row_order), 0, (0, 0), 3)]
+    one = run_all()
+    monkeypatch.setenv("SSC_CHUNK_BYTES", str(5 * n * w * 2))                  # five rows per chunk
+    many = run_all()
+    monkeypatch.delenv("SSC_CHUNK_BYTES")
+    for a, b in zip(one, many):
+        assert np.array_equal(a.data, b.data) and np.array_equal(a.irej, b.irej) and a.hi == b.hi
+        assert a.guard_fired == b.guard_fired
+        if a.coeff is not None:
+            assert np.array_equal(a.coeff, b.coeff)
+    same = port.stack_mean(fr, 2, (4.0, 3.0), 2, coeff=many[0].coeff, row_order=row_order, sd_mode=port.SD_EXACT)
+    assert np.array_equal(many[0].data, same["out"]) and np.array_equal(many[0].irej, same["irej"])
+    assert np.array_equal(many[4].data, port.stack_sum(rnd, row_order=row_order)["out"])
+    st = [port.frame_stats_sorted(f) for f in small]
+    assert st[1][2] == 65535.0 and st[0][2] == 255.0
+    assert np.allclose(many[8].coeff, port.norm_coeffs(3, [x[0] for x in st], [x[1] for x in st]), rtol=1e-11)
