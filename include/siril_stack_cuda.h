@@ -131,7 +131,28 @@ typedef struct ssc_sequence_view {
 	const int *shiftx, *shifty;	/* regparam[get_registration_layer()][i].shiftx/.shifty indexed by
 					   sequence image index; both NULL = no registration data */
 	const double *exposure;		/* per-image exposure, may be NULL (result exposure = 0) */
+	/* --- the frames as they lie in the files: decoded on the device behind the copy --- */
+	int frame_format;		/* SSC_FRAMES_*: how the bytes behind frames[] are read (0 = native WORDs);
+					   frames[i] points at the first sample (the FITS data unit / the SER frame),
+					   e.g. into the mmap()ed file */
+	int ser_bytes_per_sample;	/* SSC_FRAMES_SER_RGB: 1 or 2 (ser.c:327-329) */
+	int ser_big_endian;		/* SSC_FRAMES_SER_RGB, 16 bit: the header's flag as Siril reads it (ser.h:31-42) */
+	int ser_bgr;			/* SSC_FRAMES_SER_RGB: colour id 101, planes in reverse order (ser.c:954-957) */
+	/* --- preprocess (src/core/siril.c:945-962) fused into the load: master frames as planar
+	 * WORD [nb_layers][ry][rx] in host memory, rows in the storage order of the decoded frames; NULL = not used --- */
+	const WORD *pp_offset;		/* USE_OFFSET: g = max(g - offset, 0) */
+	const WORD *pp_dark;		/* USE_DARK without optimisation: g = max(g - dark, 0) */
+	const WORD *pp_flat;		/* USE_FLAT: g = round_to_WORD(level * (g / max(flat, 1))) (fdiv, siril.c:252-275) */
+	float pp_flat_level;		/* fdiv's coef */
 } ssc_sequence_view;
+
+enum {
+	SSC_FRAMES_U16 = 0,		/* planar WORD [nb_layers][ry][rx] (also SER 16-bit mono, little endian) */
+	SSC_FRAMES_FITS16 = 1,		/* FITS data unit, BITPIX 16 + BZERO 32768: big-endian signed samples, planar */
+	SSC_FRAMES_RAW8 = 2,		/* planar 8-bit samples: FITS BITPIX 8 data unit, SER 8-bit mono */
+	SSC_FRAMES_RAW16_BE = 3,	/* planar big-endian unsigned 16-bit: SER 16-bit mono with the big-endian flag */
+	SSC_FRAMES_SER_RGB = 4		/* SER colour frames (id 100 / 101): interleaved samples, ser_* say how */
+};
 
 /* The view is copied; the frames it points at must stay valid while operators run. */
 int ssc_bind_sequence(const sequence *seq, const ssc_sequence_view *view);
@@ -311,6 +332,40 @@ int ssc_dev_norm_coeffs_gathered(ssc_peer_group *g, int n_frames, int ref_image,
 int ssc_dev_counters_combine(ssc_peer_group *g, const uint64_t *local, uint64_t *total, void *stream);
 /* *maxim (device uint64_t) = max over the ranks, between K1 and K1b (stacking.c:311-313, 328-330) */
 int ssc_dev_max_combine(ssc_peer_group *g, unsigned long long *maxim, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* File formats either side of the path                 */
+/* ------------------------------------------------------------------------- */
+/* What readfits learns from a FITS header (image_format_fits.c:40-130), from the first bytes of the file
+ * (len = bytes available; the whole file or at least the header). */
+typedef struct ssc_fits_info {
+	int bitpix, naxis;
+	long naxes[3];			/* rx, ry, layers (1 or 3) */
+	double bzero, bscale, exposure;	/* EXPTIME / EXPOSURE */
+	WORD hi, lo;			/* MIPS-HI / MIPS-LO */
+	size_t data_offset, data_bytes;	/* the data unit */
+	int frame_format;		/* SSC_FRAMES_FITS16 or SSC_FRAMES_RAW8 */
+} ssc_fits_info;
+int ssc_fits_parse_header(const void *bytes, size_t len, ssc_fits_info *info);
+/* ser_read_header (ser.c:291-350) from the 178 header bytes; file_size fixes a missing frame count (:336-345) */
+typedef struct ssc_ser_info {
+	int color_id, big_endian, width, height, bit_depth, frame_count;
+	int bytes_per_sample, planes;
+	size_t frame_bytes, data_offset;	/* frame i starts at data_offset + i * frame_bytes */
+	int frame_format;		/* SSC_FRAMES_* of its frames; row order SSC_ROWS_SER */
+} ssc_ser_info;
+int ssc_ser_parse_header(const void *bytes, size_t file_size, ssc_ser_info *info);
+/* savefits (image_format_fits.c:652-739) of a stacking result: BITPIX 16, BZERO 32768, samples encoded on the
+ * device.  data: host, planar [layers][ry][rx] (ssc_result.data). */
+int ssc_savefits(const char *path, const WORD *data, int rx, int ry, int layers, WORD hi, WORD lo, double exposure,
+		int overwrite);
+const char *ssc_io_last_error(void);
+/* the decoders and preprocess on samples that are already on the device (what the operators run behind their uploads) */
+int ssc_dev_decode_fits16(WORD *samples, size_t count, void *stream);		/* in place */
+int ssc_dev_decode_ser(const void *raw, WORD *planes, size_t layer_stride, size_t pixels, int bytes_per_sample,
+		int big_endian, int color_id, void *stream);
+int ssc_dev_preprocess(WORD *samples, size_t count, const WORD *offset, const WORD *dark, const WORD *flat,
+		float level, void *stream);
 
 /* Counter-based synthetic frames for benchmarks and large-size
  * property tests: fills device WORD [n_frames][layers][rows][width] with storage

@@ -32,6 +32,7 @@ _lib = C.CDLL(LIB_PATH)
 NO_REJEC, PERCENTILE, SIGMA, SIGMEDIAN, WINSORIZED, LINEARFIT = range(6)
 NO_NORM, ADDITIVE, MULTIPLICATIVE, ADDITIVE_SCALING, MULTIPLICATIVE_SCALING = range(5)
 ROWS_FITS, ROWS_SER = 0, 1
+FRAMES_U16, FRAMES_FITS16, FRAMES_RAW8, FRAMES_RAW16_BE, FRAMES_SER_RGB = range(5)
 HIST_STRIDE = 65540
 N_COUNTERS = 8
 
@@ -86,7 +87,21 @@ class SequenceView(C.Structure):
         ("frames", C.POINTER(C.c_void_p)), ("frames_on_device", C.c_int),
         ("shiftx", C.POINTER(C.c_int)), ("shifty", C.POINTER(C.c_int)),
         ("exposure", C.POINTER(C.c_double)),
+        ("frame_format", C.c_int), ("ser_bytes_per_sample", C.c_int), ("ser_big_endian", C.c_int), ("ser_bgr", C.c_int),
+        ("pp_offset", C.c_void_p), ("pp_dark", C.c_void_p), ("pp_flat", C.c_void_p), ("pp_flat_level", C.c_float),
     ]
+
+
+class FitsInfo(C.Structure):
+    _fields_ = [("bitpix", C.c_int), ("naxis", C.c_int), ("naxes", C.c_long * 3), ("bzero", C.c_double), ("bscale", C.c_double),
+                ("exposure", C.c_double), ("hi", C.c_ushort), ("lo", C.c_ushort), ("data_offset", C.c_size_t),
+                ("data_bytes", C.c_size_t), ("frame_format", C.c_int)]
+
+
+class SerInfo(C.Structure):
+    _fields_ = [("color_id", C.c_int), ("big_endian", C.c_int), ("width", C.c_int), ("height", C.c_int), ("bit_depth", C.c_int),
+                ("frame_count", C.c_int), ("bytes_per_sample", C.c_int), ("planes", C.c_int), ("frame_bytes", C.c_size_t),
+                ("data_offset", C.c_size_t), ("frame_format", C.c_int)]
 
 
 class Result(C.Structure):
@@ -132,6 +147,8 @@ EXPORTS = [
     "ssc_peer_destroy", "ssc_peer_world", "ssc_peer_rank", "ssc_peer_status", "ssc_peer_last_error",
     "ssc_dev_histogram_scatter", "ssc_dev_ikss_gather", "ssc_dev_norm_coeffs_gathered",
     "ssc_dev_counters_combine", "ssc_dev_max_combine",
+    "ssc_fits_parse_header", "ssc_ser_parse_header", "ssc_savefits", "ssc_io_last_error",
+    "ssc_dev_decode_fits16", "ssc_dev_decode_ser", "ssc_dev_preprocess",
 ]
 
 _lib.ssc_last_error.restype = C.c_char_p
@@ -172,6 +189,13 @@ _lib.ssc_dev_norm_coeffs_gathered.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_
                                               C.c_void_p]
 _lib.ssc_dev_counters_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.ssc_dev_max_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+_lib.ssc_io_last_error.restype = C.c_char_p
+_lib.ssc_fits_parse_header.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(FitsInfo)]
+_lib.ssc_ser_parse_header.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(SerInfo)]
+_lib.ssc_savefits.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_ushort, C.c_ushort, C.c_double, C.c_int]
+_lib.ssc_dev_decode_fits16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+_lib.ssc_dev_decode_ser.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]
+_lib.ssc_dev_preprocess.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
 _libc = C.CDLL(None)
 _libc.free.argtypes = [C.c_void_p]
 
@@ -229,8 +253,12 @@ class Sequence:
     _next_handle = 0x1000
 
     def __init__(self, frames, reference_image=-1, row_order=ROWS_FITS, shiftx=None, shifty=None,
-                 exposure=None, on_device=False, shape=None):
-        if on_device:
+                 exposure=None, on_device=False, shape=None, frame_format=FRAMES_U16, ser_bytes_per_sample=0,
+                 ser_big_endian=0, ser_bgr=0, pp_offset=None, pp_dark=None, pp_flat=None, pp_flat_level=1.0):
+        """frame_format != FRAMES_U16: frames is a list of raw pointers (ints) to each frame's first sample as it lies
+        in the file (FITS data unit / SER frame), shape = (number, layers, ry, rx); pp_*: preprocess masters, uint16
+        [layers, ry, rx]."""
+        if on_device or frame_format != FRAMES_U16:
             self._keep = frames
             number, layers, ry, rx = shape
             ptrs = [int(p) for p in frames]
@@ -254,9 +282,12 @@ class Sequence:
         self._exp = None if exposure is None else (C.c_double * number)(*[float(v) for v in exposure])
         Sequence._next_handle += 16
         self.handle = Sequence._next_handle	# stands in for the `sequence *` key
+        self._masters = [None if m is None else np.ascontiguousarray(m, dtype=np.uint16) for m in (pp_offset, pp_dark, pp_flat)]
+        mp = [None if m is None else m.ctypes.data for m in self._masters]
         view = SequenceView(number, layers, rx, ry, reference_image, row_order,
                             C.cast(self._ptrs, C.POINTER(C.c_void_p)), int(on_device),
-                            self._sx, self._sy, self._exp)
+                            self._sx, self._sy, self._exp, frame_format, ser_bytes_per_sample, ser_big_endian, ser_bgr,
+                            mp[0], mp[1], mp[2], float(pp_flat_level))
         rc = _lib.ssc_bind_sequence(self.handle, C.byref(view))
         if rc:
             raise StackError(rc, "ssc_bind_sequence")
@@ -523,3 +554,38 @@ class PeerGroup:
         if self.h:
             _lib.ssc_peer_destroy(self.h)
             self.h = None
+
+
+class IoError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        msg = _lib.ssc_io_last_error()
+        super().__init__("%s returned %d: %s" % (where, code, msg.decode() if msg else ""))
+
+
+def fits_parse_header(buf):
+    """ssc_fits_parse_header on a bytes-like object holding (at least) the header of a FITS file."""
+    raw = (C.c_char * len(buf)).from_buffer_copy(buf)
+    info = FitsInfo()
+    rc = _lib.ssc_fits_parse_header(raw, len(buf), C.byref(info))
+    if rc:
+        raise IoError(rc, "ssc_fits_parse_header")
+    return info
+
+
+def ser_parse_header(buf, file_size=None):
+    raw = (C.c_char * len(buf)).from_buffer_copy(buf)
+    info = SerInfo()
+    rc = _lib.ssc_ser_parse_header(raw, len(buf) if file_size is None else file_size, C.byref(info))
+    if rc:
+        raise IoError(rc, "ssc_ser_parse_header")
+    return info
+
+
+def savefits(path, data, hi=0, lo=0, exposure=0.0, overwrite=True):
+    """ssc_savefits: data uint16 [layers, ry, rx] (a StackResult's .data)."""
+    data = np.ascontiguousarray(data, dtype=np.uint16)
+    layers, ry, rx = data.shape
+    rc = _lib.ssc_savefits(os.fsencode(path), data.ctypes.data, rx, ry, layers, hi, lo, float(exposure), int(overwrite))
+    if rc:
+        raise IoError(rc, "ssc_savefits")

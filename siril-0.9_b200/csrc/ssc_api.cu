@@ -210,6 +210,11 @@ int ssc_bind_sequence(const sequence *seq, const ssc_sequence_view *view) {
 	if (!seq || !view || !view->frames) return fail(SSC_ERR_ARG, "null sequence view");
 	if (view->number < 1 || view->rx < 1 || view->ry < 1 || (view->nb_layers != 1 && view->nb_layers != 3))
 		return fail(SSC_ERR_ARG, "bad sequence geometry");
+	if (view->frame_format < SSC_FRAMES_U16 || view->frame_format > SSC_FRAMES_SER_RGB) return fail(SSC_ERR_ARG, "unknown frame format");
+	if (view->frame_format != SSC_FRAMES_U16 && view->frames_on_device) return fail(SSC_ERR_ARG, "device-resident frames must be native WORDs");
+	if (view->frame_format == SSC_FRAMES_SER_RGB && (view->nb_layers != 3 || (view->ser_bytes_per_sample != 1 && view->ser_bytes_per_sample != 2)))
+		return fail(SSC_ERR_ARG, "SER colour frames have three planes of 1 or 2 bytes per sample");
+	if ((view->pp_offset || view->pp_dark || view->pp_flat) && view->frames_on_device) return fail(SSC_ERR_ARG, "preprocess masters go with host frames");
 	auto bp = std::make_shared<Bound>();
 	Bound &b = *bp;
 	b.view = *view;
@@ -305,19 +310,21 @@ struct Buf {
 
 struct DevCache {
 	cudaStream_t copy = nullptr, comp = nullptr, out = nullptr;	// upload, kernels, download
-	Buf frames, outb, hist, scratch, acc, stats, coeff, status, shifts, counters, maxim, flags;
+	cudaEvent_t t0 = nullptr, t1 = nullptr;				// the upload's duration
+	Buf frames, outb, hist, scratch, acc, stats, coeff, status, shifts, counters, maxim, flags, staging, masters;
 	std::vector<cudaEvent_t> events;
 	ssc_peer_group *group = nullptr;	// this device's end of the NVLink exchanges (several devices only)
 	std::vector<int> group_ids;
 	int group_frames = 0;
 	void release() {
-		Buf *all[] = {&frames, &outb, &hist, &scratch, &acc, &stats, &coeff, &status, &shifts, &counters, &maxim, &flags};
+		Buf *all[] = {&frames, &outb, &hist, &scratch, &acc, &stats, &coeff, &status, &shifts, &counters, &maxim, &flags, &staging, &masters};
 		for (Buf *b : all) b->release();
 		for (cudaEvent_t e : events) cudaEventDestroy(e);
 		events.clear();
 		if (group) ssc_peer_destroy(group);
 		group = nullptr;
 		for (cudaStream_t *s : {&copy, &comp, &out}) { if (*s) cudaStreamDestroy(*s); *s = nullptr; }
+		for (cudaEvent_t *e : {&t0, &t1}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
 	}
 	int event(size_t i, cudaEvent_t &e) {
 		while (events.size() <= i) {
@@ -346,6 +353,8 @@ struct Dev {
 	int *status = nullptr, *shifts = nullptr;
 	unsigned long long *counters = nullptr, *maxim = nullptr;	// counters: [layers][SSC_COUNTERS]
 	ssc_peer_group *group = nullptr;
+	unsigned char *staging = nullptr;	// raw bytes of one unit of every frame (formats that are not decoded in place)
+	WORD *masters = nullptr;		// preprocess masters of the current piece: [offset, dark, flat][C][buf_rows][W]
 	int rc = SSC_OK;
 	std::string err;
 	double t_h2d = 0, t_dev = 0, t_d2h = 0;
@@ -410,24 +419,84 @@ void piece_band(const Plan &pl, const Dev &d, const Piece &pc, ssc_band &band) {
 	band.shifty = pl.shifted ? d.shifts + pl.N : nullptr;
 }
 
-// upload the source rows of result rows [row0, row0 + rows) of one layer of every frame into the piece's band
+// `bytes` bytes of every frame, starting `src_off` bytes into it, to dst + f * dst_pitch: one pitched copy when
+// the frames are equally spaced in host memory, one copy per frame otherwise
+int copy_frames(const Plan &pl, void *dst, size_t dst_pitch, size_t src_off, size_t bytes, cudaStream_t st) {
+	const cudaMemcpyKind kind = pl.job->seq->view.frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	if (pl.strided) {
+		const char *src = (const char *) pl.job->seq->frames[pl.job->images[0]] + src_off;
+		return cudaMemcpy2DAsync(dst, dst_pitch, src, pl.host_stride, bytes, (size_t) pl.N, kind, st) == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
+	}
+	for (int f = 0; f < pl.N; f++) {
+		const char *src = (const char *) pl.job->seq->frames[pl.job->images[f]];
+		if (!src) return SSC_ERR_GENERIC;
+		if (cudaMemcpyAsync((char *) dst + (size_t) f * dst_pitch, src + src_off, bytes, kind, st) != cudaSuccess) return SSC_ERR_CUDA;
+	}
+	return SSC_OK;
+}
+
+// upload the source rows of result rows [row0, row0 + rows) of one layer of every frame into the piece's band,
+// decode them from the file's format and run preprocess on them -- all on the copy stream, so whatever waits
+// for the unit's event sees calibrated WORDs
 int upload_rows(const Plan &pl, Dev &d, const ssc_band &band, int layer, int row0, int rows, cudaStream_t st) {
 	const ssc_sequence_view &v = pl.job->seq->view;
 	int s0, sr;
 	source_rows(*pl.job, row0, rows, pl.H, s0, sr);
-	const cudaMemcpyKind kind = v.frames_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	const size_t count = (size_t) sr * pl.W;		// samples per frame and layer
 	WORD *dst = d.frames + (size_t) layer * band.layer_stride + (size_t) (s0 - band.buf_row0) * pl.W;
-	const size_t src_off = ((size_t) layer * pl.H + s0) * pl.W, bytes = (size_t) sr * pl.W * sizeof(WORD);
-	if (pl.strided) {	// equally spaced frames: one pitched copy for all of them
-		const WORD *src = pl.job->seq->frames[pl.job->images[0]] + src_off;
-		if (cudaMemcpy2DAsync(dst, band.frame_stride * sizeof(WORD), src, pl.host_stride, bytes, (size_t) pl.N, kind, st) != cudaSuccess)
-			return SSC_ERR_CUDA;
-		return SSC_OK;
+	const size_t pitch = band.frame_stride * sizeof(WORD);
+	int first_layer = layer, n_layers = 1;
+	switch (v.frame_format) {
+	case SSC_FRAMES_U16:
+	case SSC_FRAMES_FITS16:
+	case SSC_FRAMES_RAW16_BE: {
+		int rc = copy_frames(pl, dst, pitch, ((size_t) layer * pl.H + s0) * pl.W * sizeof(WORD), count * sizeof(WORD), st);
+		if (rc) return rc;
+		if (v.frame_format != SSC_FRAMES_U16
+				&& (rc = ssc::launch_decode_inplace(dst, band.frame_stride, pl.N, count, v.frame_format == SSC_FRAMES_FITS16 ? 1 : 2, st)))
+			return rc;
+		break;
 	}
-	for (int f = 0; f < pl.N; f++) {
-		const WORD *src = pl.job->seq->frames[pl.job->images[f]];
-		if (!src) return SSC_ERR_GENERIC;
-		if (cudaMemcpyAsync(dst + (size_t) f * band.frame_stride, src + src_off, bytes, kind, st) != cudaSuccess) return SSC_ERR_CUDA;
+	case SSC_FRAMES_RAW8: {
+		int rc = copy_frames(pl, d.staging, count, ((size_t) layer * pl.H + s0) * pl.W, count, st);
+		if (rc) return rc;
+		if ((rc = ssc::launch_decode_raw(d.staging, count, dst, band.frame_stride, band.layer_stride, pl.N, count, 1, 1, 0, 0, 0, st))) return rc;
+		break;
+	}
+	default: {	// SSC_FRAMES_SER_RGB: the three colours of a row are interleaved -- they arrive with layer 0
+		if (layer != 0) return SSC_OK;
+		const size_t raw = count * 3 * v.ser_bytes_per_sample;
+		int rc = copy_frames(pl, d.staging, raw, (size_t) s0 * pl.W * 3 * v.ser_bytes_per_sample, raw, st);
+		if (rc) return rc;
+		if ((rc = ssc::launch_decode_raw(d.staging, raw, dst, band.frame_stride, band.layer_stride, pl.N, count, v.ser_bytes_per_sample, 3,
+				v.ser_big_endian, v.ser_bgr, 0, st))) return rc;
+		n_layers = 3;
+		break;
+	}
+	}
+	if (d.masters) {	// preprocess (siril.c:945-962) on what was just decoded
+		const size_t mplane = (size_t) pl.C * band.layer_stride;	// one master of this piece
+		for (int c = first_layer; c < first_layer + n_layers; c++) {
+			const size_t at = (size_t) c * band.layer_stride + (size_t) (s0 - band.buf_row0) * pl.W;
+			int rc = ssc::launch_preprocess(d.frames + at, band.frame_stride, pl.N, count, v.pp_offset ? d.masters + at : nullptr,
+					v.pp_dark ? d.masters + mplane + at : nullptr, v.pp_flat ? d.masters + 2 * mplane + at : nullptr, v.pp_flat_level, st);
+			if (rc) return rc;
+		}
+	}
+	return SSC_OK;
+}
+
+// the preprocess masters' rows of a piece, once per piece (on the copy stream, ahead of the piece's units)
+int upload_masters(const Plan &pl, Dev &d, const ssc_band &band, cudaStream_t st) {
+	if (!d.masters) return SSC_OK;
+	const ssc_sequence_view &v = pl.job->seq->view;
+	const WORD *src[3] = {v.pp_offset, v.pp_dark, v.pp_flat};
+	const size_t mplane = (size_t) pl.C * band.layer_stride;
+	for (int m = 0; m < 3; m++) {
+		if (!src[m]) continue;
+		for (int c = 0; c < pl.C; c++)
+			if (cudaMemcpyAsync(d.masters + m * mplane + (size_t) c * band.layer_stride, src[m] + ((size_t) c * pl.H + band.buf_row0) * pl.W,
+					band.layer_stride * sizeof(WORD), cudaMemcpyHostToDevice, st) != cudaSuccess) return SSC_ERR_CUDA;
 	}
 	return SSC_OK;
 }
@@ -538,6 +607,7 @@ int device_run(const Plan &pl, Dev &d, int phase) {
 			ssc_band piece;
 			piece_band(pl, d, pc, piece);
 			if (!resident) {	// the accumulators of other pieces were overwritten: this piece's sums again
+				DRC(upload_masters(pl, d, piece, dc.comp), "upload failed");
 				for (int c = 0; c < pl.C; c++) DRC(upload_rows(pl, d, piece, c, pc.row0, pc.rows, dc.comp), "upload failed");
 				for (const Unit &u : d.units)
 					if (u.piece == (int) k) DRC(ssc::launch_sum_accumulate([&] { ssc_band ub; unit_band(piece, u, ub); return ub; }(),
@@ -560,6 +630,7 @@ int device_run(const Plan &pl, Dev &d, int phase) {
 			ssc_band piece;
 			piece_band(pl, d, pc, piece);
 			const auto t0 = std::chrono::steady_clock::now();
+			DRC(upload_masters(pl, d, piece, dc.comp), "upload failed");
 			for (int c = 0; c < pl.C; c++) DRC(upload_rows(pl, d, piece, c, pc.row0, pc.rows, dc.comp), "upload failed");
 			DCU(cudaStreamSynchronize(dc.comp));
 			d.t_h2d += ms_since(t0);
@@ -583,12 +654,15 @@ int device_run(const Plan &pl, Dev &d, int phase) {
 		if (resident && pl.need_norm)	// layer 0 first: the statistics only need that one
 			std::stable_sort(mine.begin(), mine.end(), [&](size_t a, size_t b) { return (d.units[a].layer != 0) < (d.units[b].layer != 0); });
 		const auto t_up = std::chrono::steady_clock::now();
+		if (resident) DCU(cudaEventRecord(dc.t0, dc.copy));
+		DRC(upload_masters(pl, d, piece, dc.copy), "upload failed");
 		for (size_t i : mine) {	// the copy stream runs ahead of everything else
 			const Unit &u = d.units[i];
 			DRC(upload_rows(pl, d, piece, u.layer, u.row0, u.rows, dc.copy), "upload failed");
 			DRC(new_event(up[i]), "event");
 			DCU(cudaEventRecord(up[i], dc.copy));
 		}
+		if (resident) DCU(cudaEventRecord(dc.t1, dc.copy));
 		if (resident && pl.need_norm) {
 			// K4 behind the copy front, layer 0 chunk by chunk
 			for (size_t i : mine) {
@@ -634,19 +708,19 @@ int device_run(const Plan &pl, Dev &d, int phase) {
 				DCU(cudaEventRecord(down[i], dc.out));
 			}
 		}
-		if (resident) {
-			DCU(cudaStreamSynchronize(dc.copy));
-			d.t_h2d += ms_since(t_up);
-		}
-		const auto t_k = std::chrono::steady_clock::now();
 		if (streamed_out) {
-			for (size_t i : mine) {	// every unit's rows into the caller's image as they arrive
+			for (size_t i : mine) {	// every unit's rows into the caller's image as they arrive (under the upload)
 				DCU(cudaEventSynchronize(down[i]));
 				land(pl, d.units[i].layer, d.units[i].row0, d.units[i].rows);
 			}
 		}
 		DCU(cudaStreamSynchronize(dc.comp));
-		d.t_dev += ms_since(t_k);	// what is left after the upload: the last unit's kernel and download
+		if (resident) {	// how long the upload took, and what was left to do when it ended
+			DCU(cudaStreamSynchronize(dc.copy));
+			float ms = 0.0f;
+			if (!mine.empty() && cudaEventElapsedTime(&ms, dc.t0, dc.t1) == cudaSuccess) d.t_h2d += ms;
+			d.t_dev += std::max(0.0, ms_since(t_up) - (double) ms);
+		}
 		if (*pl.cancel) return SSC_ERR_GENERIC;
 	}
 	return SSC_OK;
@@ -656,6 +730,10 @@ int run_job(const Job &job) {
 	using clk = std::chrono::steady_clock;
 	const auto t_begin = clk::now();
 	static const bool trace = getenv("SSC_TRACE") != nullptr;	// phase timeline on stderr (debug aid)
+	static clk::time_point t_last_exit = t_begin;
+	struct ExitStamp { clk::time_point &t; ~ExitStamp() { t = clk::now(); } } exit_stamp{t_last_exit};
+	if (trace) fprintf(stderr, "[ssc trace] %8.3f ms since the previous operator call returned\n",
+			std::chrono::duration<double, std::milli>(t_begin - t_last_exit).count());
 	auto mark = [&](const char *what) {
 		if (trace) fprintf(stderr, "[ssc trace] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(clk::now() - t_begin).count(), what);
 	};
@@ -693,7 +771,7 @@ int run_job(const Job &job) {
 			if (!p) return fail(SSC_ERR_GENERIC, "frame %d has no data", job.images[f]);
 			if (p - f0 != st * f) pl.strided = false;
 		}
-		if (st < (ptrdiff_t) (plane * C * sizeof(WORD))) pl.strided = false;
+		if (st <= 0) pl.strided = false;
 		pl.host_stride = (size_t) st;
 	}
 
@@ -762,6 +840,8 @@ int run_job(const Job &job) {
 		}
 		for (cudaStream_t *s : {&dc.copy, &dc.comp, &dc.out})
 			if (!*s) CU(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
+		for (cudaEvent_t *e : {&dc.t0, &dc.t1})
+			if (!*e) CU(cudaEventCreate(e));
 #define SSC_ENSURE(buf, bytes) do { if (dc.buf.ensure(bytes)) return fail(SSC_ERR_CUDA, "device allocation of %zu bytes failed", (size_t) (bytes)); } while (0)
 		SSC_ENSURE(frames, (size_t) N * C * d.max_buf_rows * W * sizeof(WORD));
 		SSC_ENSURE(outb, (size_t) C * d.max_rows * W * sizeof(WORD));
@@ -776,6 +856,18 @@ int run_job(const Job &job) {
 			const unsigned long long neutral = job.op == OP_ADDMIN ? 0xFFFFull : 0ull;	// low word = the extreme kernels' unsigned int
 			CU(cudaMemcpyAsync(d.maxim, &neutral, sizeof(neutral), cudaMemcpyHostToDevice, dc.comp));
 			CU(cudaStreamSynchronize(dc.comp));
+		}
+		if (v.frame_format == SSC_FRAMES_RAW8 || v.frame_format == SSC_FRAMES_SER_RGB) {
+			int max_src = 1;	// source rows of the largest unit
+			for (const Unit &u : d.units) { int s0, sr; source_rows(job, u.row0, u.rows, H, s0, sr); max_src = std::max(max_src, sr); }
+			for (const Piece &pc : d.pieces) { int s0, sr; source_rows(job, pc.row0, pc.rows, H, s0, sr); if (d.pieces.size() > 1 || job.want_coeff_only) max_src = std::max(max_src, sr); }
+			const size_t per_sample = v.frame_format == SSC_FRAMES_SER_RGB ? 3 * (size_t) v.ser_bytes_per_sample : 1;
+			SSC_ENSURE(staging, (size_t) N * max_src * W * per_sample);
+			d.staging = (unsigned char *) dc.staging.p;
+		}
+		if (v.pp_offset || v.pp_dark || v.pp_flat) {
+			SSC_ENSURE(masters, (size_t) 3 * C * d.max_buf_rows * W * sizeof(WORD));
+			d.masters = (WORD *) dc.masters.p;
 		}
 		if (job.op == OP_SUM) {
 			SSC_ENSURE(acc, (size_t) C * d.max_rows * W * sizeof(uint32_t));

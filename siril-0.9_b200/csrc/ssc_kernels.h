@@ -71,6 +71,14 @@ int launch_ikss(const uint32_t *hist, int n_frames, double *stats, uint32_t *scr
 int launch_norm_coeffs(const double *stats, int n_frames, int ref_image, int mode, double *coeff,
 		int *status, cudaStream_t stream);
 
+// ssc_io.cu: decoding of the file formats and preprocess, on rows of every frame of a band
+// mode 1: FITS BITPIX 16 + BZERO 32768 (byte swap, sign flip), 2: big-endian unsigned (byte swap)
+int launch_decode_inplace(WORD *base, size_t frame_stride, int n_frames, size_t count, int mode, cudaStream_t st);
+int launch_decode_raw(const void *raw, size_t raw_frame_bytes, WORD *dst, size_t frame_stride, size_t layer_stride,
+		int n_frames, size_t count, int bytes, int colours, int big_endian, int bgr, int signed_bzero, cudaStream_t st);
+int launch_preprocess(WORD *base, size_t frame_stride, int n_frames, size_t count, const WORD *offset, const WORD *dark,
+		const WORD *flat, float level, cudaStream_t st);
+
 // ssc_synth.cu
 int launch_synth(WORD *frames, int n_frames, int layers, int rows, int width, int first_frame,
 		int row0, int full_height, int kind, uint64_t seed, cudaStream_t stream);
