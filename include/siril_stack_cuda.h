@@ -359,6 +359,13 @@ int ssc_ser_parse_header(const void *bytes, size_t file_size, ssc_ser_info *info
  * device.  data: host, planar [layers][ry][rx] (ssc_result.data). */
 int ssc_savefits(const char *path, const WORD *data, int rx, int ry, int layers, WORD hi, WORD lo, double exposure,
 		int overwrite);
+/* statistics(fit, layer, NULL, STATS_BASIC, STATS_ZERO_NULLCHECK) (src/algos/statistics.c:207-326) for every layer
+ * of an image, as noise() (src/core/siril.c:1740-1771) and the stacking summary run it on the result: the fields of
+ * imstats (src/core/siril.h:600-605) that STATS_BASIC fills.  data: host, planar [layers][ry][rx]. */
+typedef struct ssc_imstats {
+	double total, ngoodpix, mean, median, sigma, bgnoise, min, max, normValue;
+} ssc_imstats;
+int ssc_image_statistics(const WORD *data, int rx, int ry, int layers, int nullcheck, ssc_imstats *stats);
 const char *ssc_io_last_error(void);
 /* the decoders and preprocess on samples that are already on the device (what the operators run behind their uploads) */
 int ssc_dev_decode_fits16(WORD *samples, size_t count, void *stream);		/* in place */

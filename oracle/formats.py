@@ -103,3 +103,53 @@ def preprocess(frame, offset=None, dark=None, flat=None, level=1.0):
         t = np.float64(np.float32(level)) * (g.astype(np.float64) / f)
         g = np.where(t <= 0, 0, np.where(t > 65535.0, 65535, np.floor(t + 0.5))).astype(np.int64)
     return g.astype(np.uint16)
+
+
+def basic_statistics(layer, nullcheck=True):
+    """statistics(fit, layer, NULL, STATS_BASIC, STATS_ZERO_NULLCHECK) (src/algos/statistics.c:207-326) of one uint16
+    [H, W] layer.  median: siril_stats_ushort_median (:47-64); min / max: gsl_stats_ushort_minmax over the non-zero
+    pixels.  ngoodpix / mean / sigma / bgnoise come from cfitsio's fits_img_stats_ushort, which is NOT part of
+    /root/reference: FnMeanSigma (mean = sum / n, sigma = sqrt(sum2 / n - mean^2) over the non-null pixels) and FnNoise1
+    (per row: sigma of the differences of consecutive non-null pixels with three passes of 5-sigma clipping; the median
+    over the rows that have at least two differences; times 0.70710678) are restated from its published source --
+    parity unpinned."""
+    h, w = layer.shape
+    data = layer.ravel()
+    good = data[data != 0] if nullcheck else data
+    n = good.size
+    if n == 0:
+        return None
+    g = good.astype(np.float64)
+    mean = g.sum() / n
+    sigma = np.sqrt((g * g).sum() / n - mean * mean) if n > 1 else 0.0
+    hist = np.bincount(data, minlength=65536).astype(np.float64)
+    run, median = 0.0, 0.0
+    for i in range(1 if nullcheck else 0, 65536):
+        run += hist[i]
+        if run > n * 0.5:
+            median = float(i)
+            break
+    sds = []
+    for row in layer:
+        vals = row[row != 0] if nullcheck else row
+        if vals.size < 3:
+            continue
+        d = (vals[:-1].astype(np.int64) - vals[1:].astype(np.int64)).astype(np.float32).astype(np.float64)
+        m, sd = d.mean(), np.sqrt(max((d * d).sum() / d.size - d.mean() ** 2, 0.0))
+        if sd > 0.0:
+            for _ in range(3):
+                keep = np.abs(d - m) < 5.0 * sd
+                if keep.all():
+                    break
+                d = d[keep]
+                if d.size > 1:
+                    m, sd = d.sum() / d.size, np.sqrt(max((d * d).sum() / d.size - (d.sum() / d.size) ** 2, 0.0))
+                elif d.size == 1:
+                    m, sd = d[0], 0.0
+                else:
+                    m, sd = 0.0, 0.0
+        sds.append(sd)
+    sds = np.sort(np.array(sds))
+    noise = 0.0 if sds.size == 0 else (sds[0] if sds.size == 1 else (sds[(sds.size - 1) // 2] + sds[sds.size // 2]) / 2.0)
+    return dict(total=float(h * w), ngoodpix=float(n), mean=mean, median=median, sigma=sigma, bgnoise=0.70710678 * noise,
+                min=float(good.min()), max=float(good.max()))

@@ -148,7 +148,7 @@ EXPORTS = [
     "ssc_dev_histogram_scatter", "ssc_dev_ikss_gather", "ssc_dev_norm_coeffs_gathered",
     "ssc_dev_counters_combine", "ssc_dev_max_combine",
     "ssc_fits_parse_header", "ssc_ser_parse_header", "ssc_savefits", "ssc_io_last_error",
-    "ssc_dev_decode_fits16", "ssc_dev_decode_ser", "ssc_dev_preprocess",
+    "ssc_dev_decode_fits16", "ssc_dev_decode_ser", "ssc_dev_preprocess", "ssc_image_statistics",
 ]
 
 _lib.ssc_last_error.restype = C.c_char_p
@@ -195,6 +195,7 @@ _lib.ssc_ser_parse_header.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(SerInfo)
 _lib.ssc_savefits.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_ushort, C.c_ushort, C.c_double, C.c_int]
 _lib.ssc_dev_decode_fits16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
 _lib.ssc_dev_decode_ser.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]
+_lib.ssc_image_statistics.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
 _lib.ssc_dev_preprocess.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
 _libc = C.CDLL(None)
 _libc.free.argtypes = [C.c_void_p]
@@ -554,6 +555,21 @@ class PeerGroup:
         if self.h:
             _lib.ssc_peer_destroy(self.h)
             self.h = None
+
+
+class ImStats(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("total", "ngoodpix", "mean", "median", "sigma", "bgnoise", "min", "max", "normValue")]
+
+
+def image_statistics(data, nullcheck=True):
+    """ssc_image_statistics: STATS_BASIC of every layer of uint16 [layers, ry, rx] -> list of dicts."""
+    data = np.ascontiguousarray(data, dtype=np.uint16)
+    layers, ry, rx = data.shape
+    st = (ImStats * 3)()
+    rc = _lib.ssc_image_statistics(data.ctypes.data, rx, ry, layers, int(nullcheck), st)
+    if rc:
+        raise IoError(rc, "ssc_image_statistics")
+    return [{k: getattr(st[c], k) for k, _ in ImStats._fields_} for c in range(layers)]
 
 
 class IoError(RuntimeError):

@@ -791,7 +791,9 @@ int run_job(const Job &job) {
 		const int rows = H / G + (g < H % G ? 1 : 0);
 		CU(cudaSetDevice(d.id));
 		size_t free_b = 0, total_b = 0;
+		mark("plan: device selected");
 		CU(cudaMemGetInfo(&free_b, &total_b));
+		mark("plan: cudaMemGetInfo");
 		DevCache &dc = g_cache[d.id];
 		d.dc = &dc;
 		free_b += dc.frames.cap + dc.outb.cap + dc.hist.cap + dc.scratch.cap + dc.acc.cap;	// what this library already holds is reusable
@@ -851,6 +853,7 @@ int run_job(const Job &job) {
 		d.frames = (WORD *) dc.frames.p; d.out = (WORD *) dc.outb.p;
 		d.counters = (unsigned long long *) dc.counters.p; d.coeff = (double *) dc.coeff.p;
 		d.maxim = (unsigned long long *) dc.maxim.p;
+		mark("plan: buffers ensured");
 		CU(cudaMemsetAsync(d.counters, 0, (size_t) 3 * SSC_COUNTERS * sizeof(unsigned long long), dc.comp));
 		{
 			const unsigned long long neutral = job.op == OP_ADDMIN ? 0xFFFFull : 0ull;	// low word = the extreme kernels' unsigned int
@@ -869,6 +872,7 @@ int run_job(const Job &job) {
 			SSC_ENSURE(masters, (size_t) 3 * C * d.max_buf_rows * W * sizeof(WORD));
 			d.masters = (WORD *) dc.masters.p;
 		}
+		mark("plan: neutral element set");
 		if (job.op == OP_SUM) {
 			SSC_ENSURE(acc, (size_t) C * d.max_rows * W * sizeof(uint32_t));
 			d.acc = (uint32_t *) dc.acc.p;

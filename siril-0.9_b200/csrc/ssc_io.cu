@@ -17,6 +17,7 @@
 //       flat 0 -> 1 (fdiv, :252-275); applied to the decoded rows before anything else sees them.
 //   savefits (image_format_fits.c:652-739, save_fits_header :741-): header cards as cfitsio writes
 //       them, the samples encoded on the GPU.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -309,3 +310,200 @@ int ssc_dev_preprocess(WORD *samples, size_t count, const WORD *offset, const WO
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// After the stack: statistics(fit, layer, NULL, STATS_BASIC, STATS_ZERO_NULLCHECK)
+// (src/algos/statistics.c:207-326), which noise() (src/core/siril.c:1740-1771) and the stacking
+// summary run on the result.  Everything but the noise estimate follows from the layer's exact histogram
+// (K4 again): the count of non-zero pixels, their mean and sigma from the integer sums of k h[k] and
+// k^2 h[k], min, max, and siril_stats_ushort_median (statistics.c:47-64) -- the first bin where the
+// running count exceeds n / 2.  The noise estimate is cfitsio's (fits_img_stats_ushort, "noise1": per
+// row, the 5-sigma clipped standard deviation of the differences of consecutive non-null pixels, three
+// clipping passes; the median over the rows, divided by sqrt 2).  cfitsio is not part of
+// /root/reference: that estimator is restated from its published source, "parity unpinned".
+// ---------------------------------------------------------------------------------------------
+namespace ssc {
+
+__global__ void __launch_bounds__(1024)
+k_basic_stats(const uint32_t *__restrict__ hist, int nullcheck, double total, ssc_imstats *__restrict__ out) {
+	const uint32_t *h = hist + (size_t) blockIdx.x * SSC_HIST_STRIDE;
+	__shared__ unsigned long long s_n[32], s_s[32], s_q[32];
+	__shared__ unsigned int s_min, s_max, s_wsum[32], s_median;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) { s_min = 0xFFFFFFFFu; s_max = 0; s_median = 0; }
+	__syncthreads();
+	// thread t owns bins [64 t, 64 t + 64)
+	unsigned long long n = 0, s = 0, q = 0;
+	unsigned int lo = 0xFFFFFFFFu, hi = 0;
+	for (int k = 0; k < 64; k++) {
+		const unsigned int bin = (unsigned int) tid * 64 + k;
+		const unsigned long long c = (nullcheck && bin == 0) ? 0ull : h[bin];
+		if (c) { n += c; s += c * bin; q += c * bin * bin; lo = min(lo, bin); hi = max(hi, bin); }
+	}
+	const unsigned int mine = (unsigned int) n;	// (a layer holds fewer than 2^32 pixels)
+	for (int o = 16; o > 0; o >>= 1) {
+		n += __shfl_xor_sync(0xffffffffu, n, o);
+		s += __shfl_xor_sync(0xffffffffu, s, o);
+		q += __shfl_xor_sync(0xffffffffu, q, o);
+		lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+		hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+	}
+	if (lane == 0) { s_n[warp] = n; s_s[warp] = s; s_q[warp] = q; atomicMin(&s_min, lo); atomicMax(&s_max, hi); }
+	// exclusive prefix of the per-thread counts: where does the running count pass n / 2 ?
+	unsigned int inc = mine;
+	for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+	if (lane == 31) s_wsum[warp] = inc;
+	__syncthreads();
+	unsigned long long N = 0, S = 0, Q = 0;
+	unsigned int before = 0;
+	for (int w = 0; w < 32; w++) { N += s_n[w]; S += s_s[w]; Q += s_q[w]; if (w < warp) before += s_wsum[w]; }
+	const unsigned int excl = before + inc - mine;
+	const double half = dmul((double) (long long) N, 0.5);		// (double) n * 0.5, statistics.c:58
+	if ((double) excl <= half && (double) (excl + mine) > half) {	// the crossing is inside my bins
+		unsigned int run = excl;
+		for (int k = 0; k < 64; k++) {
+			const unsigned int bin = (unsigned int) tid * 64 + k;
+			run += (nullcheck && bin == 0) ? 0u : h[bin];
+			if ((double) run > half) { s_median = bin; break; }
+		}
+	}
+	__syncthreads();
+	if (tid == 0) {
+		ssc_imstats r;
+		r.total = total;
+		r.ngoodpix = (double) (long long) N;
+		const double nn = (double) (long long) N;
+		const double mean = N ? ddiv((double) (long long) S, nn) : 0.0;
+		r.mean = mean;
+		r.sigma = N > 1 ? dsqrt(dsub(ddiv(__ull2double_rn(Q), nn), dmul(mean, mean))) : 0.0;	// FnMeanSigma
+		r.median = (double) s_median;
+		r.min = N ? (double) s_min : 0.0;
+		r.max = (double) s_max;
+		r.bgnoise = 0.0;
+		r.normValue = 0.0;
+		out[blockIdx.x] = r;
+	}
+}
+
+// one block per row: the 5-sigma clipped standard deviation of the first differences (FnNoise1)
+constexpr int NOISE_THREADS = 256, NOISE_PER_THREAD = 64;	// rows up to 16384 pixels
+__global__ void __launch_bounds__(NOISE_THREADS)
+k_row_noise(const WORD *__restrict__ img, int width, int nullcheck, double *__restrict__ row_sd) {
+	const WORD *row = img + (size_t) blockIdx.x * width;
+	const int tid = threadIdx.x;
+	const int per = (width + NOISE_THREADS - 1) / NOISE_THREADS;	// consecutive pixels per thread
+	const int x0 = tid * per, x1 = min(width, x0 + per);
+	__shared__ int s_last[NOISE_THREADS];		// my last valid pixel's value, -1: none
+	__shared__ double s_a[NOISE_THREADS], s_b[NOISE_THREADS];
+	__shared__ int s_c[NOISE_THREADS];
+	int last = -1;
+	for (int x = x0; x < x1; x++) { const int v = row[x]; if (!nullcheck || v != 0) last = v; }
+	s_last[tid] = last;
+	__syncthreads();
+	int prev = -1;					// the valid pixel before my first one
+	for (int t = tid - 1; t >= 0 && prev < 0; t--) prev = s_last[t];
+	float d[NOISE_PER_THREAD];
+	unsigned long long alive = 0;
+	int nd = 0;
+	for (int x = x0; x < x1 && nd < NOISE_PER_THREAD; x++) {
+		const int v = row[x];
+		if (nullcheck && v == 0) continue;
+		if (prev >= 0) { d[nd] = (float) (prev - v); alive |= 1ull << nd; nd++; }
+		prev = v;
+	}
+	auto reduce = [&](double &sum, double &sum2, int &cnt) {
+		double a = 0.0, b = 0.0;
+		int c = 0;
+#pragma unroll 8
+		for (int k = 0; k < NOISE_PER_THREAD; k++)
+			if (k < nd && (alive >> k & 1ull)) { const double v = (double) d[k]; a += v; b += v * v; c++; }
+		s_a[tid] = a; s_b[tid] = b; s_c[tid] = c;
+		__syncthreads();
+		for (int o = NOISE_THREADS / 2; o > 0; o >>= 1) {
+			if (tid < o) { s_a[tid] += s_a[tid + o]; s_b[tid] += s_b[tid + o]; s_c[tid] += s_c[tid + o]; }
+			__syncthreads();
+		}
+		sum = s_a[0]; sum2 = s_b[0]; cnt = s_c[0];
+		__syncthreads();
+	};
+	double sum, sum2;
+	int cnt;
+	reduce(sum, sum2, cnt);
+	double sd = -1.0;				// rows with fewer than two differences do not count
+	if (cnt >= 2) {
+		double mean = sum / cnt;
+		sd = sqrt(fmax(sum2 / cnt - mean * mean, 0.0));
+		if (sd > 0.0)
+			for (int iter = 0; iter < 3; iter++) {
+				const int before = cnt;
+				for (int k = 0; k < nd; k++)
+					if ((alive >> k & 1ull) && !(fabs((double) d[k] - mean) < 5.0 * sd)) alive &= ~(1ull << k);
+				reduce(sum, sum2, cnt);
+				if (cnt == before) break;
+				if (cnt > 1) { mean = sum / cnt; sd = sqrt(fmax(sum2 / cnt - mean * mean, 0.0)); }
+				else if (cnt == 1) { mean = sum; sd = 0.0; }
+				else { mean = 0.0; sd = 0.0; }
+			}
+	}
+	if (tid == 0) row_sd[blockIdx.x] = sd;
+}
+
+}  // namespace ssc
+
+extern "C" int ssc_image_statistics(const WORD *data, int rx, int ry, int layers, int nullcheck, ssc_imstats *stats) {
+	if (!data || !stats || rx < 1 || ry < 1 || layers < 1 || layers > 3) return io_fail(SSC_ERR_ARG, "bad image");
+	if (rx > NOISE_THREADS * NOISE_PER_THREAD) return io_fail(SSC_ERR_ARG, "rows longer than 16384 pixels are not supported");
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1) return io_fail(SSC_ERR_CUDA, "no CUDA device available");
+	const size_t plane = (size_t) rx * ry;
+	WORD *d_img = nullptr;
+	uint32_t *d_hist = nullptr;
+	ssc_imstats *d_stats = nullptr;
+	double *d_rows = nullptr;
+	std::vector<double> rows((size_t) layers * ry);
+	cudaError_t e = cudaMalloc(&d_img, plane * layers * sizeof(WORD));
+	if (e == cudaSuccess) e = cudaMalloc(&d_hist, (size_t) layers * SSC_HIST_STRIDE * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMalloc(&d_stats, layers * sizeof(ssc_imstats));
+	if (e == cudaSuccess) e = cudaMalloc(&d_rows, rows.size() * sizeof(double));
+	if (e == cudaSuccess) e = cudaMemcpy(d_img, data, plane * layers * sizeof(WORD), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemset(d_hist, 0, (size_t) layers * SSC_HIST_STRIDE * sizeof(uint32_t));
+	int rc = SSC_OK;
+	if (e == cudaSuccess) {
+		ssc_band b{};	// every layer as a one-layer "frame": K4 histograms layer 0 of every frame
+		b.frames = d_img;
+		b.frame_stride = plane;
+		b.layer_stride = plane;
+		b.n_frames = layers;
+		b.layers = 1;
+		b.width = rx;
+		b.height = ry;
+		b.buf_rows = b.out_rows = ry;
+		rc = launch_histogram(b, d_hist, nullptr);
+		if (!rc) {
+			k_basic_stats<<<layers, 1024>>>(d_hist, nullcheck, (double) plane, d_stats);
+			k_row_noise<<<layers * ry, NOISE_THREADS>>>(d_img, rx, nullcheck, d_rows);
+			e = cudaGetLastError();
+		}
+	}
+	if (e == cudaSuccess && !rc) e = cudaMemcpy(stats, d_stats, layers * sizeof(ssc_imstats), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && !rc) e = cudaMemcpy(rows.data(), d_rows, rows.size() * sizeof(double), cudaMemcpyDeviceToHost);
+	cudaFree(d_img); cudaFree(d_hist); cudaFree(d_stats); cudaFree(d_rows);
+	if (rc) return io_fail(rc, "histogram launch failed");
+	if (e != cudaSuccess) return io_fail(SSC_ERR_CUDA, "statistics failed: %s", cudaGetErrorString(e));
+	WORD mx = 0;	// get_normalized_value (utils.c:454-459): 255 when no layer has a sample above it
+	for (int c = 0; c < layers; c++) mx = std::max<WORD>(mx, (WORD) stats[c].max);
+	for (int c = 0; c < layers; c++) {
+		std::vector<double> sd;
+		for (int y = 0; y < ry; y++) if (rows[(size_t) c * ry + y] >= 0.0) sd.push_back(rows[(size_t) c * ry + y]);
+		double noise = 0.0;
+		if (sd.size() == 1) noise = sd[0];
+		else if (sd.size() > 1) {	// the median over the rows
+			std::sort(sd.begin(), sd.end());
+			noise = (sd[(sd.size() - 1) / 2] + sd[sd.size() / 2]) / 2.0;
+		}
+		stats[c].bgnoise = 0.70710678 * noise;
+		stats[c].normValue = mx <= 255 ? 255.0 : 65535.0;
+		if (stats[c].ngoodpix < 1.0) return io_fail(SSC_ERR_GENERIC, "no data computed");	// statistics() returns NULL (:247-250)
+	}
+	return SSC_OK;
+}

@@ -15,6 +15,7 @@ struct LeftoverList {
 	unsigned int *count;		// items appended
 	unsigned int capacity;		// = every pixel of the launch: the list cannot overflow
 	unsigned int *ids;		// [capacity] indices of the pixels in the band ((layer * out_rows + row) * width + x)
+	unsigned int *next_tile;	// work counter of the launch (ssc_stack_fast.cu: warp tiles are handed out dynamically)
 };
 
 // append one pixel index per flagged lane: one atomic per warp
@@ -44,7 +45,7 @@ inline int leftover_ids(unsigned long long pixels, LeftoverList &list, cudaStrea
 	cudaGetDevice(&dev);
 	if (dev < 0 || dev >= 64 || pixels > 0xFFFFFFF0ull) return SSC_ERR_ARG;
 	LeftoverIdStore &st = g_leftover_id_store[dev];
-	if (!st.count && cudaMalloc(&st.count, sizeof(unsigned int)) != cudaSuccess) return SSC_ERR_CUDA;
+	if (!st.count && cudaMalloc(&st.count, 2 * sizeof(unsigned int)) != cudaSuccess) return SSC_ERR_CUDA;
 	if (st.capacity < pixels) {
 		if (st.ids) cudaFree(st.ids);
 		st.ids = nullptr;
@@ -52,10 +53,11 @@ inline int leftover_ids(unsigned long long pixels, LeftoverList &list, cudaStrea
 		if (cudaMalloc(&st.ids, (size_t) pixels * sizeof(unsigned int)) != cudaSuccess) return SSC_ERR_CUDA;
 		st.capacity = (size_t) pixels;
 	}
-	if (cudaMemsetAsync(st.count, 0, sizeof(unsigned int), stream) != cudaSuccess) return SSC_ERR_CUDA;
+	if (cudaMemsetAsync(st.count, 0, 2 * sizeof(unsigned int), stream) != cudaSuccess) return SSC_ERR_CUDA;
 	list.count = st.count;
 	list.capacity = (unsigned int) pixels;
 	list.ids = st.ids;
+	list.next_tile = st.count + 1;
 	return SSC_OK;
 }
 

@@ -211,7 +211,7 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 	auto locate = [&](unsigned long long t, int &lay, int &rr, int &x2, int &x_warp) -> bool {
 		// (fast_path_eligible guarantees 32-bit pixel counts and frame strides: no 64-bit division)
 		if constexpr (ROWTILE) {
-			const unsigned int wt = (unsigned int) t * (FAST_THREADS / 32) + warp;
+			const unsigned int wt = (unsigned int) t;	// (ROWTILE: tiles are warp tiles, handed out one by one)
 			const unsigned int n_wt = (unsigned int) b.layers * (unsigned int) b.out_rows * xblocks;
 			const unsigned int wc = wt < n_wt ? wt : n_wt - 1;
 			const unsigned int row = wc / xblocks, xb = wc - row * xblocks;
@@ -273,13 +273,28 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 		}
 		asm volatile("cp.async.commit_group;" ::: "memory");
 	};
-	if (PREFETCH && !punt_all && blockIdx.x < n_tiles) issue_tile(blockIdx.x);
+	// ROWTILE: every warp draws its next warp tile from the launch's work counter, so a launch ends with at most
+	// one tile per warp outstanding whatever its size (a band of 1/8 of the image left a partial wave of
+	// statically assigned tiles: 0.60 ms for the work of 0.54)
+	auto next_after = [&](unsigned long long t) -> unsigned long long {
+		if constexpr (ROWTILE) {
+			unsigned int n = 0;
+			if (lane == 0) n = atomicAdd(list.next_tile, 1u);
+			return __shfl_sync(0xffffffffu, n, 0);
+		} else {
+			return t + gridDim.x;
+		}
+	};
+	unsigned long long first_tile = ROWTILE ? next_after(0) : blockIdx.x;
+	if (PREFETCH && !punt_all && first_tile < n_tiles) issue_tile(first_tile);
 	// Blocks loop over tiles (the launcher bounds the grid): the tables, the coefficient copy and
 	// their barriers above are paid once per block instead of once per tile.
 	// (MODE_SIGMA_REG runs one more round after its last tile, to drain the warp queues)
-	for (unsigned long long tile = blockIdx.x; ; tile += gridDim.x) {
+	unsigned long long upcoming = 0;
+	for (unsigned long long tile = first_tile; ; tile = upcoming) {
 	const bool more = tile < n_tiles;
 	if (MODE != MODE_SIGMA_REG && !more) break;
+	upcoming = more ? next_after(tile) : tile;
 	if (more) {
 	unsigned long long g = tile * FAST_THREADS + tid;
 	bool active = g < total;
@@ -328,7 +343,7 @@ k_stack_fast(StackParams p, LeftoverList list, unsigned int n_tiles) {
 		for (int k = 0; k < NP; k++) v[k] = stage_t[k * stage_stride];
 		have_q = true;
 		if constexpr (ROWTILE) __syncwarp();	// everybody has its column: the buffer may be refilled
-		if (PREFETCH && tile + gridDim.x < n_tiles) issue_tile(tile + gridDim.x);
+		if (PREFETCH && upcoming < n_tiles) issue_tile(upcoming);
 	} else {
 	if (!active) g = total - 1;
 	const int x2 = (int) (g % W2);
@@ -747,10 +762,10 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 		return SSC_ERR_CUDA;
 	// ROWTILE: tiles of four warp tiles, each 32 consecutive pairs of one row
 	const unsigned long long tiles = ROWTILE
-			? ((unsigned long long) b.layers * b.out_rows * (((b.width >> 1) + 31) / 32) + FAST_THREADS / 32 - 1) / (FAST_THREADS / 32)
+			? (unsigned long long) b.layers * b.out_rows * (((b.width >> 1) + 31) / 32)
 			: (total + FAST_THREADS - 1) / FAST_THREADS;
 	if (tiles > 0x7FFFFFFFull) return SSC_ERR_ARG;
-	unsigned long long blocks = tiles;
+	unsigned long long blocks = ROWTILE ? (tiles + FAST_THREADS / 32 - 1) / (FAST_THREADS / 32) : tiles;
 	{	// a bounded grid of looping blocks: 8 per resident slot for big launches, 4 for small ones (measured;
 		// a block should keep a few dozen tiles to amortise its prologue).  SSC_FAST_WAVES overrides.
 		int dev = 0, sms = 148, per_sm = 1;
@@ -761,11 +776,11 @@ static int launch_fast_cfg(const StackParams &p, cudaStream_t stream) {
 		static int forced = -1;
 		if (forced < 0) { const char *e = getenv("SSC_FAST_WAVES"); forced = e ? atoi(e) : 0; if (forced < 0) forced = 0; }
 		const unsigned long long slots = (unsigned long long) sms * per_sm;
-		const int waves = forced ? forced : (tiles / slots >= 256 ? 8 : 4);
+		const int waves = ROWTILE ? 1 : (forced ? forced : (tiles / slots >= 256 ? 8 : 4));	// ROWTILE: the resident warps draw their tiles
 		const unsigned long long cap = slots * waves;
 		if (blocks > cap) blocks = cap;
 	}
-	LeftoverList list{nullptr, 0, nullptr};
+	LeftoverList list{nullptr, 0, nullptr, nullptr};
 	if (MODE == MODE_SIGMA_REG) {
 		int rc = leftover_ids(total * 2, list, stream);
 		if (rc) return rc;

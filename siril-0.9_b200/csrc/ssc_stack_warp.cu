@@ -6,9 +6,9 @@
 // one flag per sample.  The reference (gsl_fit_linear) evaluates it as 4 N strictly sequential
 // running-mean updates; one thread per pixel doing the same waits on a single FP64 dependency chain
 // (408 ms for cfg5 in round 1's form).  Here a warp owns the column:
-//   1. the block stages a tile of 8 pixel pairs x N frames in shared memory with 4-byte cp.async
-//      (16 consecutive pixels of a row: whole 32-byte sectors), each warp reads its pair's column
-//      conflict-free, lane l taking frames l, l+32, ... and normalizing them (exact FP64);
+//   1. lane l loads the pair's samples of frames l, l+32, ... (4 bytes per frame; the warps of the grid work
+//      on consecutive pairs at the same time, so the sectors are shared through the L2) and normalizes them
+//      (exact FP64);
 //   2. the column is sorted in registers as packed u16x2 (both pixels at once): a Batcher network on
 //      each lane's R samples, then bitonic merges across lanes with shuffles (first stage against the
 //      reversed partner, so every run stays ascending) -- lane l ends up with sorted samples
@@ -33,7 +33,6 @@
 namespace ssc {
 
 constexpr int WARP_PAIRS = 8;		// warps per block = pixel pairs per tile
-constexpr int WARP_PITCH = 9;		// words per frame in the staging tile: odd, so a warp's column read is conflict-free
 constexpr unsigned int FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------------
@@ -229,113 +228,57 @@ __device__ __forceinline__ bool fit_pixel(const unsigned int (&v)[R], const int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// the kernel
+// the kernel: every warp on its own -- no block-wide step anywhere, because the number of clipping
+// iterations differs from pixel to pixel by a factor of four and a tile barrier made every warp wait for
+// the slowest of its block (30 % of the stall samples in the first form, profiles/r02_ncu_cfg5_warp_v2.txt).
+// Warp g takes pixel pairs g, g + (warps of the grid), ...: at any time the warps of the whole GPU work on
+// a run of consecutive pairs, so the 32-byte sectors a warp touches for its 4 bytes per frame are shared
+// with seven other warps through the L2 (DRAM bytes stay the algorithmic ones).
 // ---------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(32 * WARP_PAIRS, 2)
-k_stack_warp(StackParams p, unsigned int n_tiles, unsigned int tiles_per_row, int is_median, LeftoverList list) {
-	constexpr int NPAD = 32 * R;
-	extern __shared__ __align__(16) unsigned int stage[];	// [NPAD][WARP_PITCH] raw packed pairs, double y[warps][R][32], double coef[3][NPAD]
-	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
-	__shared__ int s_fast_norm;
+k_stack_warp(StackParams p, unsigned int n_pairs, int is_median, LeftoverList list) {
+	extern __shared__ __align__(16) double s_fit[];		// [warps][R][32] doubles: the fit's copy of a pixel's samples
 	const ssc_band &b = p.band;
 	const int W = b.width, W2 = W >> 1, N = b.n_frames, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
-	double *s_y = reinterpret_cast<double *>(stage + NPAD * WARP_PITCH) + warp * NPAD + lane;
-	double *s_coef = reinterpret_cast<double *>(stage + NPAD * WARP_PITCH) + (is_median ? 0 : WARP_PAIRS * NPAD);
-
-	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
-	if (tid == 0) s_fast_norm = 1;
-	__syncthreads();
-	if (norm) {
-		for (int f = tid; f < NPAD; f += blockDim.x) {
-			const bool have = f < N;
-			const double off = have ? p.coeff[f] : 0.0, mul = have ? p.coeff[N + f] : 1.0, sc = have ? p.coeff[2 * N + f] : 1.0;
-			s_coef[f] = off;
-			s_coef[NPAD + f] = mul;
-			s_coef[2 * NPAD + f] = sc;
-			if (have) {	// domain of the 2^52 tricks (ssc_network.cuh): every intermediate stays below 2^31
-				const bool additive = p.normalize == ADDITIVE || p.normalize == ADDITIVE_SCALING;
-				const double bound = additive ? dadd(dmul(fabs(sc), 65535.0), fabs(off)) : dmul(dmul(fabs(sc), 65535.0), fabs(mul));
-				if (!(bound < 2147483000.0)) s_fast_norm = 0;
-			}
-		}
-	}
-	__syncthreads();
-	const bool fast_norm = s_fast_norm != 0;
-	const unsigned int sbase = (unsigned int) __cvta_generic_to_shared(stage);
+	double *s_y = s_fit + (size_t) warp * 32 * R + lane;
 	const unsigned long long fstride = (unsigned long long) b.frame_stride * sizeof(WORD);
+	const unsigned int warps_total = gridDim.x * WARP_PAIRS;
+	unsigned long long cnt[SSC_COUNTERS] = {0, 0, 0, 0, 0, 0, 0, 0};	// lane 0: this warp's share of the counters
 
-	// stage a tile: thread -> (pair tid % 8, frames tid / 8, tid / 8 + 32, ...), 4-byte asynchronous copies.
-	// The next tile is requested as soon as the columns are in registers, so it lands under the sort and the fit.
-	auto issue_tile = [&](const unsigned int t) {
-		const unsigned int trow = t / tiles_per_row;
-		const int tx2_0 = (int) (t - trow * tiles_per_row) * WARP_PAIRS;
-		const int tlayer = (int) (trow / (unsigned int) b.out_rows);
-		const int tRr = b.out_row0 + (int) (trow - (unsigned int) tlayer * (unsigned int) b.out_rows);
-		const int tsrow = b.row_order == SSC_ROWS_SER ? b.height - 1 - tRr : tRr;
-		const size_t trow_words = ((size_t) tlayer * b.layer_stride + (size_t) (tsrow - b.buf_row0) * W) >> 1;
-		const int j = tid & (WARP_PAIRS - 1);
-		int x2 = tx2_0 + j;
-		if (x2 >= W2) x2 = W2 - 1;			// ragged row end: a duplicate, never written back
-		const char *src = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames) + trow_words + x2);
-		for (int f = tid >> 3; f < N; f += 32)
-			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::
-					"r"(sbase + (unsigned int) ((f * WARP_PITCH + j) * (int) sizeof(unsigned int))),
-					"l"(src + (unsigned long long) f * fstride) : "memory");
-		asm volatile("cp.async.commit_group;" ::: "memory");
-	};
-	if (blockIdx.x < n_tiles) issue_tile(blockIdx.x);
-
-	for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		const unsigned int row = tile / tiles_per_row;
-		const int x2_0 = (int) (tile - row * tiles_per_row) * WARP_PAIRS;
+	for (unsigned int pair = blockIdx.x * WARP_PAIRS + warp; pair < n_pairs; pair += warps_total) {
+		const unsigned int row = pair / (unsigned int) W2;
+		const int x2 = (int) (pair - row * (unsigned int) W2);
 		const int layer = (int) (row / (unsigned int) b.out_rows);
 		const int rr = (int) (row - (unsigned int) layer * (unsigned int) b.out_rows);
 		const int Rr = b.out_row0 + rr;				// result storage row (stacking.c:731,1600)
+		const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - Rr : Rr;
+		const char *src = reinterpret_cast<const char *>(reinterpret_cast<const unsigned int *>(b.frames)
+				+ (((size_t) layer * b.layer_stride + (size_t) (srow - b.buf_row0) * W) >> 1) + x2);
 
-		// ---- 1. the tile's samples (requested a tile ago, see issue_tile) ----
-		asm volatile("cp.async.wait_group 0;" ::: "memory");
-		__syncthreads();
-
-		// ---- normalization in place (stacking.c:1635-1652, :750-764), a rolled loop over the tile ----
-		if (norm) {
-			for (int idx = tid; idx < N * WARP_PAIRS; idx += 32 * WARP_PAIRS) {
-				const int f = idx >> 3;
-				unsigned int *slot = stage + f * WARP_PITCH + (idx & (WARP_PAIRS - 1));
-				unsigned int w = *slot;
-				const double off = s_coef[f], mul = s_coef[NPAD + f], sc = s_coef[2 * NPAD + f];
-				unsigned long long qa = 0, qb = 0;
-				if (!fast_norm) {
-					w = normalize_sample(w & 0xFFFFu, p.normalize, off, mul, sc)
-							| (normalize_sample(w >> 16, p.normalize, off, mul, sc) << 16);
-				} else {
-					switch (p.normalize) {
-					case ADDITIVE: w = normalize_pair_fast<ADDITIVE>(w, off, mul, sc, qa, qb); break;
-					case MULTIPLICATIVE: w = normalize_pair_fast<MULTIPLICATIVE>(w, off, mul, sc, qa, qb); break;
-					case ADDITIVE_SCALING: w = normalize_pair_fast<ADDITIVE_SCALING>(w, off, mul, sc, qa, qb); break;
-					default: w = normalize_pair_fast<MULTIPLICATIVE_SCALING>(w, off, mul, sc, qa, qb); break;
-					}
-				}
-				*slot = w;
-			}
-			__syncthreads();
-		}
-		// ---- my pair's column: lane l takes frames l, l + 32, ... (sentinels sort behind the samples) ----
+		// ---- 1. my pair's column: lane l takes frames l, l + 32, ... (sentinels sort behind the samples) ----
 		unsigned int v[R];
 #pragma unroll
 		for (int r = 0; r < R; r++) {
 			const int f = r * 32 + lane;
-			v[r] = f < N ? stage[f * WARP_PITCH + warp] : 0xFFFFFFFFu;
+			v[r] = f < N ? __ldg(reinterpret_cast<const unsigned int *>(src + (unsigned long long) f * fstride)) : 0xFFFFFFFFu;
 		}
-		__syncthreads();					// the staging tile may be overwritten now
-		if (tile + gridDim.x < n_tiles) issue_tile(tile + gridDim.x);
+		if (norm) {	// normalization (stacking.c:1635-1652, :750-764), the conversion-based exact form
+#pragma unroll
+			for (int r = 0; r < R; r++) {
+				const int f = r * 32 + lane;
+				if (f < N) {
+					const double off = p.coeff[f], mul = p.coeff[N + f], sc = p.coeff[2 * N + f];
+					v[r] = normalize_sample(v[r] & 0xFFFFu, p.normalize, off, mul, sc)
+							| (normalize_sample(v[r] >> 16, p.normalize, off, mul, sc) << 16);
+				}
+			}
+		}
 
 		// ---- 2. sort: lane l ends up with sorted samples [l R, (l + 1) R) of both pixels ----
 		warp_sort<R>(v, lane);
 
-		const int x2 = x2_0 + warp;
-		const bool active = x2 < W2;				// warp-uniform
 		const size_t out_idx = (size_t) layer * p.out_layer_stride + (size_t) (Rr - p.out_buf_row0) * W + 2 * (size_t) x2;
 		if (is_median) {					// stacking.c:765-767, double -> WORD truncation
 			const int m1 = (N - 1) >> 1, m2 = N >> 1;
@@ -347,38 +290,38 @@ k_stack_warp(StackParams p, unsigned int n_tiles, unsigned int tiles_per_row, in
 			}
 			a = __shfl_sync(FULL, a, m1 / R);
 			c = __shfl_sync(FULL, c, m2 / R);
-			if (active && lane == 0) {
+			if (lane == 0) {
 				const unsigned int lo = ((a & 0xFFFFu) + (c & 0xFFFFu)) >> 1, hi = ((a >> 16) + (c >> 16)) >> 1;
 				*reinterpret_cast<unsigned int *>(p.out + out_idx) = lo | (hi << 16);
 			}
 			continue;
 		}
 		// ---- 3. linear-fit clipping, one pixel of the pair after the other ----
-		if (active) {
 #pragma unroll 1
-			for (int sel = 0; sel < 2; sel++) {
-				unsigned int res = 0, rej_lo = 0, rej_hi = 0;
-				int guard = 0, cap = 0;
-				const bool done = fit_pixel<R>(v, sel, N, lane, p.sig_low, p.sig_high, p.fit, s_y, res, rej_lo, rej_hi, guard, cap);
-				if (lane == 0) {
-					if (done) {
-						p.out[out_idx + sel] = (WORD) res;
-						if (rej_lo) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) rej_lo);
-						if (rej_hi) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) rej_hi);
-						if (guard) atomicAdd(&blk_counters[6], 1ull);
-						if (cap) atomicAdd(&blk_counters[7], 1ull);
-					} else {
-						const unsigned int slot = atomicAdd(list.count, 1u);
-						if (slot < list.capacity)
-							list.ids[slot] = (unsigned int) (((size_t) layer * b.out_rows + rr) * W + 2 * x2 + sel);
-					}
+		for (int sel = 0; sel < 2; sel++) {
+			unsigned int res = 0, rej_lo = 0, rej_hi = 0;
+			int guard = 0, cap = 0;
+			const bool done = fit_pixel<R>(v, sel, N, lane, p.sig_low, p.sig_high, p.fit, s_y, res, rej_lo, rej_hi, guard, cap);
+			__syncwarp();
+			if (lane == 0) {
+				if (done) {
+					p.out[out_idx + sel] = (WORD) res;
+					cnt[layer * 2 + 0] += rej_lo;
+					cnt[layer * 2 + 1] += rej_hi;
+					cnt[6] += guard;
+					cnt[7] += cap;
+				} else {
+					const unsigned int slot = atomicAdd(list.count, 1u);
+					if (slot < list.capacity)
+						list.ids[slot] = (unsigned int) (((size_t) layer * b.out_rows + rr) * W + 2 * x2 + sel);
 				}
 			}
 		}
 	}
-	__syncthreads();
-	if (p.counters && tid < SSC_COUNTERS && blk_counters[tid])
-		atomicAdd(&p.counters[tid], blk_counters[tid]);
+	if (p.counters && lane == 0)
+#pragma unroll
+		for (int k = 0; k < SSC_COUNTERS; k++)
+			if (cnt[k]) atomicAdd(&p.counters[k], cnt[k]);
 }
 
 // Same shape conditions as the other packed-pair kernels; linear fit from 8 frames on (fewer: the
@@ -398,17 +341,13 @@ bool warp_path_eligible(const StackParams &p, int is_median) {
 template <int R>
 static int launch_warp(const StackParams &p, int is_median, cudaStream_t stream) {
 	const ssc_band &b = p.band;
-	constexpr int NPAD = 32 * R;
-	const unsigned long long tiles_per_row = ((unsigned long long) (b.width >> 1) + WARP_PAIRS - 1) / WARP_PAIRS;
-	const unsigned long long tiles = tiles_per_row * b.layers * b.out_rows;
-	if (tiles == 0) return SSC_OK;
-	if (tiles >= 0xFFFFFFF0ull) return SSC_ERR_ARG;
-	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
-	const size_t smem = (size_t) NPAD * WARP_PITCH * sizeof(unsigned int) + (norm ? (size_t) 3 * NPAD * sizeof(double) : 0)
-			+ (is_median ? 0 : (size_t) WARP_PAIRS * NPAD * sizeof(double));
+	const unsigned long long pairs = (unsigned long long) (b.width >> 1) * b.layers * b.out_rows;
+	if (pairs == 0) return SSC_OK;
+	if (pairs >= 0xFFFFFFF0ull) return SSC_ERR_ARG;
+	const size_t smem = is_median ? 0 : (size_t) WARP_PAIRS * 32 * R * sizeof(double);
 	if (cudaFuncSetAttribute(k_stack_warp<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
-	LeftoverList list{nullptr, 0, nullptr};
+	LeftoverList list{nullptr, 0, nullptr, nullptr};
 	const unsigned long long pixels = (unsigned long long) b.layers * b.out_rows * b.width;
 	if (!is_median) {
 		int rc = leftover_ids(pixels, list, stream);
@@ -419,9 +358,10 @@ static int launch_warp(const StackParams &p, int is_median, cudaStream_t stream)
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stack_warp<R>, 32 * WARP_PAIRS, smem) != cudaSuccess || per_sm < 1)
 		per_sm = 1;
-	unsigned long long blocks = (unsigned long long) sms * per_sm * 4;	// looping blocks, a few per resident slot
-	if (blocks > tiles) blocks = tiles;
-	k_stack_warp<R><<<(unsigned int) blocks, 32 * WARP_PAIRS, smem, stream>>>(p, (unsigned int) tiles, (unsigned int) tiles_per_row, is_median, list);
+	unsigned long long blocks = (unsigned long long) sms * per_sm;	// resident warps only: every warp strides over the pairs
+	const unsigned long long need = (pairs + WARP_PAIRS - 1) / WARP_PAIRS;
+	if (blocks > need) blocks = need;
+	k_stack_warp<R><<<(unsigned int) blocks, 32 * WARP_PAIRS, smem, stream>>>(p, (unsigned int) pairs, is_median, list);
 	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
 	if (!is_median)	// pixels the screening could not decide: gsl_fit_linear's literal recurrences (ssc_column.cuh)
 		return launch_stack_generic(p, list.ids, list.count, (unsigned int) pixels, 0, stream);

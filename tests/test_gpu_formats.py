@@ -20,7 +20,7 @@ def addr(buf, offset):
 def fits_sequence(gpu, frames, bitpix=16, **kw):
     """One FITS file image per frame, in memory; the sequence points at their data units."""
     files = [bytearray(formats.fits_encode(f, bitpix=bitpix)) for f in frames]
-    infos = [gpu.fits_parse_header(bytes(b[:5760])) for b in files]
+    infos = [gpu.fits_parse_header(bytes(b)) for b in files]
     n, (c, h, w) = len(frames), frames[0].shape
     assert all((i.naxes[0], i.naxes[1], i.naxes[2]) == (w, h, c) for i in infos)
     seq = gpu.Sequence([addr(b, i.data_offset) for b, i in zip(files, infos)], shape=(n, c, h, w),
@@ -141,3 +141,29 @@ def test_savefits_round_trip(gpu, tmp_path):
     gpu.savefits(path, mono)
     dec, cards, _ = formats.fits_decode(open(path, "rb").read())
     assert np.array_equal(dec, mono) and cards["NAXIS"] == "2" and "NAXIS3" not in cards
+
+
+def test_post_stack_statistics(gpu):
+    """ssc_image_statistics = statistics(STATS_BASIC, nullcheck) per layer of the stacked image (what noise() and the
+    stacking summary compute): counts, min, max and the histogram median exact; mean, sigma and the noise estimate
+    against the float64 restatement."""
+    fr = synth.make_frames(10, 3, 64, 96, seed=17, outlier_p=2e-3, zero_p=2e-3, stars=6)
+    res = gpu.stack_mean_with_rejection(gpu.Sequence(fr), 2, (4.0, 3.0), 1)
+    img = res.data.copy()
+    img[1, 5, :] = 0                                          # a dead row: no differences at all
+    img[2, 7, 3:] = 0                                         # a row with a single difference
+    st = gpu.image_statistics(img)
+    for c in range(3):
+        want = formats.basic_statistics(img[c])
+        for k in ("total", "ngoodpix", "median", "min", "max"):
+            assert st[c][k] == want[k], (c, k)
+        for k in ("mean", "sigma", "bgnoise"):
+            assert abs(st[c][k] - want[k]) <= 1e-12 * abs(want[k]), (c, k, st[c][k], want[k])
+        assert st[c]["normValue"] == 65535.0
+    low = (img[:1] >> 8).astype(np.uint16)
+    assert gpu.image_statistics(low)[0]["normValue"] == 255.0
+    with pytest.raises(gpu.IoError):
+        gpu.image_statistics(np.zeros((1, 8, 8), np.uint16))           # "Error: no data computed."
+    st0 = gpu.image_statistics(low, nullcheck=False)[0]
+    w0 = formats.basic_statistics(low[0], nullcheck=False)
+    assert st0["ngoodpix"] == low.size and st0["median"] == w0["median"] and st0["min"] == w0["min"]
