@@ -259,7 +259,7 @@ class Sequence:
         """frame_format != FRAMES_U16: frames is a list of raw pointers (ints) to each frame's first sample as it lies
         in the file (FITS data unit / SER frame), shape = (number, layers, ry, rx); pp_*: preprocess masters, uint16
         [layers, ry, rx]."""
-        if on_device or frame_format != FRAMES_U16:
+        if on_device or frame_format != FRAMES_U16 or shape is not None:
             self._keep = frames
             number, layers, ry, rx = shape
             ptrs = [int(p) for p in frames]

@@ -313,6 +313,10 @@ struct DevCache {
 	cudaEvent_t t0 = nullptr, t1 = nullptr;				// the upload's duration
 	Buf frames, outb, hist, scratch, acc, stats, coeff, status, shifts, counters, maxim, flags, staging, masters;
 	std::vector<cudaEvent_t> events;
+	// the row split of the previous call and what it was made for: cudaMemGetInfo takes 10-35 ms on a busy device,
+	// a repeated call of the same shape keeps its plan (the buffers are still there)
+	std::vector<long long> plan_key;
+	std::vector<int> plan_piece_rows;
 	ssc_peer_group *group = nullptr;	// this device's end of the NVLink exchanges (several devices only)
 	std::vector<int> group_ids;
 	int group_frames = 0;
@@ -790,31 +794,40 @@ int run_job(const Job &job) {
 		d.index = g;
 		const int rows = H / G + (g < H % G ? 1 : 0);
 		CU(cudaSetDevice(d.id));
-		size_t free_b = 0, total_b = 0;
-		mark("plan: device selected");
-		CU(cudaMemGetInfo(&free_b, &total_b));
-		mark("plan: cudaMemGetInfo");
 		DevCache &dc = g_cache[d.id];
 		d.dc = &dc;
-		free_b += dc.frames.cap + dc.outb.cap + dc.hist.cap + dc.scratch.cap + dc.acc.cap;	// what this library already holds is reusable
-		// what the library itself keeps on the device besides frames and result: histograms and IKSS scratch,
-		// 4 bytes per result pixel for the hand-back lists of the register / warp kernels, and the extra
-		// source rows the y shifts reach for (source_rows())
-		size_t fixed = (size_t) N * (SSC_HIST_STRIDE + 65536) * 4 + (64u << 20);
-		fixed += (size_t) reach * N * C * W * sizeof(WORD);
-		size_t budget = free_b > fixed ? (size_t) ((free_b - fixed) * 0.85) : 0;
-		if (const char *e = getenv("SSC_HBM_BUDGET_BYTES")) {	// tests force the row split with it
-			const unsigned long long cap = strtoull(e, nullptr, 10);
-			if (cap > 0 && cap < budget) budget = (size_t) cap;
-		}
-		const size_t per_row = (size_t) N * C * W * sizeof(WORD) + (size_t) C * W * (sizeof(WORD) + 2 * sizeof(uint32_t));
-		size_t fit_rows = per_row ? budget / per_row : 0;
-		if (fit_rows < 1) return fail(SSC_ERR_GENERIC, "not enough device memory for one row of %d frames", N);
-		const int n_pieces = (int) ((rows + fit_rows - 1) / fit_rows);
-		for (int k = 0; k < n_pieces; k++) {
-			int r = rows / n_pieces + (k < rows % n_pieces ? 1 : 0);
-			d.pieces.push_back(Piece{row, r});
-			row += r;
+		const char *budget_env = getenv("SSC_HBM_BUDGET_BYTES");
+		const std::vector<long long> key = {N, C, W, H, rows, reach, (long long) job.op, (long long) job.rejection, need_norm,
+				budget_env ? atoll(budget_env) : 0ll};
+		if (dc.plan_key == key && !dc.plan_piece_rows.empty() && dc.frames.p) {
+			for (int r : dc.plan_piece_rows) { d.pieces.push_back(Piece{row, r}); row += r; }
+		} else {
+			size_t free_b = 0, total_b = 0;
+			CU(cudaMemGetInfo(&free_b, &total_b));
+			mark("plan: cudaMemGetInfo");
+			free_b += dc.frames.cap + dc.outb.cap + dc.hist.cap + dc.scratch.cap + dc.acc.cap;	// what this library already holds is reusable
+			// what the library itself keeps on the device besides frames and result: histograms and IKSS scratch,
+			// 4 bytes per result pixel for the hand-back lists of the register / warp kernels, and the extra
+			// source rows the y shifts reach for (source_rows())
+			size_t fixed = (size_t) N * (SSC_HIST_STRIDE + 65536) * 4 + (64u << 20);
+			fixed += (size_t) reach * N * C * W * sizeof(WORD);
+			size_t budget = free_b > fixed ? (size_t) ((free_b - fixed) * 0.85) : 0;
+			if (budget_env) {	// tests force the row split with it
+				const unsigned long long cap = strtoull(budget_env, nullptr, 10);
+				if (cap > 0 && cap < budget) budget = (size_t) cap;
+			}
+			const size_t per_row = (size_t) N * C * W * sizeof(WORD) + (size_t) C * W * (sizeof(WORD) + 2 * sizeof(uint32_t));
+			size_t fit_rows = per_row ? budget / per_row : 0;
+			if (fit_rows < 1) return fail(SSC_ERR_GENERIC, "not enough device memory for one row of %d frames", N);
+			const int n_pieces = (int) ((rows + fit_rows - 1) / fit_rows);
+			dc.plan_piece_rows.clear();
+			for (int k = 0; k < n_pieces; k++) {
+				int r = rows / n_pieces + (k < rows % n_pieces ? 1 : 0);
+				d.pieces.push_back(Piece{row, r});
+				dc.plan_piece_rows.push_back(r);
+				row += r;
+			}
+			dc.plan_key = key;
 		}
 		for (size_t k = 0; k < d.pieces.size(); k++) {
 			const Piece &pc = d.pieces[k];
