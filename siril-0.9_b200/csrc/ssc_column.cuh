@@ -41,6 +41,15 @@ __device__ __forceinline__ double column_median(Column c, int o, int n) {
 	return dmul((double) (int) (a + c.get(o + rhs)), 0.5);	// x / 2.0 == x * 0.5 exactly
 }
 
+// fabs(sigma - sigma0) / sigma0 > 0.0005 (stacking.c:1728) without the division wherever the answer is not within
+// 1e-9 of the limit (the quotient's own rounding is 1e-16): there the reference's expression is evaluated
+__device__ __forceinline__ bool relative_change_exceeds(double sigma, double sigma0) {
+	const double diff = fabs(dsub(sigma, sigma0)), lim = dmul(0.0005, sigma0);
+	if (diff > dmul(lim, 1.000000001)) return true;
+	if (diff < dmul(lim, 0.999999999)) return false;
+	return ddiv(diff, sigma0) > 0.0005;
+}
+
 // One flag-and-remove pass of SIGMA / WINSORIZED (stacking.c:1680-1693, 1731-1747)
 // on the sorted survivors c[o .. o+N).  Returns the number of samples removed.
 __device__ __forceinline__ int sigma_pass_sorted(Column c, int &o, int &N, double slow, double shigh,
@@ -212,7 +221,7 @@ static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int
 				sigma0 = sigma;
 				sigma = dmul(1.134, sd_from_sums<SMALLN>(Sw, Qw, N, tables));
 				if (++inner >= SSC_ITER_CAP) { st.cap = 1; break; }
-			} while (ddiv(fabs(dsub(sigma, sigma0)), sigma0) > 0.0005);
+			} while (relative_change_exceeds(sigma, sigma0));
 			n = sigma_pass_sorted(c, o, N, slow, shigh, sigma, median, r, S, Q, st);
 			if (++iter >= SSC_ITER_CAP) { st.cap = 1; break; }
 		} while (n > 0 && N > 3);

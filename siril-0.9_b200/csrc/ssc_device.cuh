@@ -75,7 +75,7 @@ __device__ __forceinline__ double sd_from_sums(unsigned long long S, unsigned lo
 	const unsigned long long D = (unsigned long long) n * Q - S * S;
 	double var, nn1;
 	if constexpr (SMALLN) {
-		// D < n^2 * 2^32 <= 2^44: exact through the 2^52 mantissa trick, no conversion unit
+		// D < n^2 * 2^32 <= 2^52 (n <= 1024): exact through the 2^52 mantissa trick, no conversion unit
 		const double d = dsub(__hiloint2double(0x43300000 | (int) (D >> 32), (int) (unsigned int) D), 4503599627370496.0);
 		var = div_exact(d, (double) (n * n), t->inv_n2[n]);
 		nn1 = t->unbias[n];

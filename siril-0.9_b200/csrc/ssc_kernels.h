@@ -15,6 +15,8 @@ struct FitTables {
 	const double *mx;	// gsl_fit_linear's running mean of x_i = i after n steps (data independent)
 	const double *mdx2;	// its running mean of (i - mx[n])^2 after n steps
 	const double *inv_den;	// RN(12 / (n^2 (n^2 - 1))): 1 / (n Sxx - Sx^2) of x_i = i (ssc_stack_warp.cu)
+	const double *unbias;	// n / (n - 1), the reference's own quotient in gsl_stats_ushort_sd's last step
+	const double *inv_n2;	// RN(1 / n^2): with inv they are ssc_device.cuh's SmallN tables for n <= 1024 (ssc_stack_mid.cu)
 	int n_max;		// 0: no tables, literal divisions
 };
 

@@ -150,10 +150,12 @@ int launch_stack_generic(const StackParams &p, const unsigned int *list, const u
 // FitTables (ssc_kernels.h): built once per device with the literal recurrences of gsl_fit_linear
 // for x_i = i, so that looking them up gives the very bits the per-pixel loops would compute.
 // ---------------------------------------------------------------------------
-__global__ void k_fit_tables(double *inv, double *mx, double *mdx2, double *inv_den, int n_max) {
+__global__ void k_fit_tables(double *inv, double *mx, double *mdx2, double *inv_den, double *unbias, double *inv_n2, int n_max) {
 	const int n = blockIdx.x * blockDim.x + threadIdx.x;
 	if (n > n_max) return;
-	if (n == 0) { inv[0] = 0.0; mx[0] = 0.0; mdx2[0] = 0.0; inv_den[0] = 0.0; return; }
+	if (n == 0) { inv[0] = 0.0; mx[0] = 0.0; mdx2[0] = 0.0; inv_den[0] = 0.0; unbias[0] = 0.0; inv_n2[0] = 0.0; return; }
+	unbias[n] = n > 1 ? ddiv((double) n, (double) (n - 1)) : 0.0;
+	inv_n2[n] = ddiv(1.0, dmul((double) n, (double) n));
 	{
 		const double n2 = dmul((double) n, (double) n);	// n^2 (n^2 - 1) / 12 is an integer below 2^41: exact
 		inv_den[n] = n > 1 ? ddiv(1.0, ddiv(dmul(n2, dsub(n2, 1.0)), 12.0)) : 0.0;
@@ -169,7 +171,7 @@ __global__ void k_fit_tables(double *inv, double *mx, double *mdx2, double *inv_
 	mdx2[n] = m_dx2;
 }
 
-static double *g_fit_store[64];	// per device: [4][SSC_GENERIC_MAX_FRAMES + 1]
+static double *g_fit_store[64];	// per device: [6][SSC_GENERIC_MAX_FRAMES + 1]
 
 static int fit_tables(FitTables &fit, cudaStream_t stream) {
 	int dev = 0;
@@ -178,10 +180,10 @@ static int fit_tables(FitTables &fit, cudaStream_t stream) {
 	const int n_max = SSC_GENERIC_MAX_FRAMES, stride = n_max + 1;
 	if (!g_fit_store[dev]) {
 		double *t = nullptr;
-		if (cudaMalloc(&t, (size_t) 4 * stride * sizeof(double)) != cudaSuccess) return SSC_ERR_CUDA;
+		if (cudaMalloc(&t, (size_t) 6 * stride * sizeof(double)) != cudaSuccess) return SSC_ERR_CUDA;
 		// built on the launching stream: ordered before the kernel that reads it; later launches on
 		// other streams of this device come after this call returned, hence the synchronisation
-		k_fit_tables<<<(stride + 127) / 128, 128, 0, stream>>>(t, t + stride, t + 2 * stride, t + 3 * stride, n_max);
+		k_fit_tables<<<(stride + 127) / 128, 128, 0, stream>>>(t, t + stride, t + 2 * stride, t + 3 * stride, t + 4 * stride, t + 5 * stride, n_max);
 		if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { cudaFree(t); return SSC_ERR_CUDA; }
 		g_fit_store[dev] = t;
 	}
@@ -189,6 +191,8 @@ static int fit_tables(FitTables &fit, cudaStream_t stream) {
 	fit.mx = g_fit_store[dev] + stride;
 	fit.mdx2 = g_fit_store[dev] + 2 * stride;
 	fit.inv_den = g_fit_store[dev] + 3 * stride;
+	fit.unbias = g_fit_store[dev] + 4 * stride;
+	fit.inv_n2 = g_fit_store[dev] + 5 * stride;
 	fit.n_max = n_max;
 	return SSC_OK;
 }
@@ -219,8 +223,10 @@ static ScratchOwner g_scratch_owner[64];
 
 static int launch_stack_unchained(const StackParams &p_in, int is_median, cudaStream_t stream) {
 	StackParams p = p_in;
-	p.fit = FitTables{nullptr, nullptr, nullptr, nullptr, 0};
-	if (!is_median && p.rejection == LINEARFIT) {
+	p.fit = FitTables{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+	// the per-n tables: gsl_fit_linear's data-independent recurrences for the linear fit, and the reciprocals that
+	// take the divisions out of sigma / mean for 65..1024 frames (ssc_stack_mid.cu)
+	if (!is_median && (p.rejection == LINEARFIT || (p.rejection != NO_REJEC && g_kernel_path != 1 && mid_path_eligible(p, is_median)))) {
 		int rc = fit_tables(p.fit, stream);
 		if (rc) return rc;
 	}

@@ -267,7 +267,10 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 			} else {
 				RejectState st{0, 0, 0, 0};
 				const unsigned long long S = s_S[tid] + s_S[2 * MID_THREADS + tid], Q = s_Q[tid] + s_Q[2 * MID_THREADS + tid];
-				res = reject_sorted_and_mean<false>(c, N, p.rejection, p.sig_low, p.sig_high, S, Q, st, nullptr, &p.fit);
+				// (n <= 1024: n Q - S^2 < 2^52, the domain of the table-driven sigma / mean of ssc_device.cuh)
+				const SmallN tables{p.fit.unbias, p.fit.inv, p.fit.inv_n2};
+				res = p.fit.unbias ? reject_sorted_and_mean<true>(c, N, p.rejection, p.sig_low, p.sig_high, S, Q, st, &tables, &p.fit)
+						: reject_sorted_and_mean<false>(c, N, p.rejection, p.sig_low, p.sig_high, S, Q, st, nullptr, &p.fit);
 				if (active) {
 					if (st.rej_lo) atomicAdd(&blk_counters[layer * 2 + 0], (unsigned long long) st.rej_lo);
 					if (st.rej_hi) atomicAdd(&blk_counters[layer * 2 + 1], (unsigned long long) st.rej_hi);
