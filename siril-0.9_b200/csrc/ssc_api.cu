@@ -400,6 +400,8 @@ struct Plan {
 	size_t plane;
 	const std::atomic<bool> *cancel;
 	std::shared_future<void> result_ready;	// the result's pages have been touched (see run_job)
+	std::chrono::steady_clock::time_point t_begin;
+	bool trace;
 };
 
 // the device-resident band of a piece
@@ -522,8 +524,9 @@ int histogram_rows(const Plan &pl, Dev &d, const ssc_band &piece, int row0, int 
 	ssc_band hb = piece;
 	hb.out_row0 = piece.row_order == SSC_ROWS_SER ? pl.H - (row0 + rows) : row0;
 	hb.out_rows = rows;
-	return ssc::launch_histogram_ex(hb, d.group ? nullptr : d.hist, d.group ? ssc::peer_frame_hist(d.group) : nullptr, d.flags,
-			layer0_only, st);
+	uint32_t *hist = d.hist;
+	if (d.group && ssc::peer_local_histograms(d.group, pl.N, &hist, st)) return SSC_ERR_CUDA;
+	return ssc::launch_histogram_ex(hb, hist, nullptr, d.flags, layer0_only, st);
 }
 
 // K5 + K6 once this device's counts are complete; the coefficients end up in d.coeff on every device
@@ -602,6 +605,10 @@ int device_run(const Plan &pl, Dev &d, int phase) {
 	DCU(cudaSetDevice(d.id));
 	const bool resident = d.pieces.size() == 1;
 	const auto t_begin = std::chrono::steady_clock::now();
+	auto dmark = [&](const char *what) {
+		if (pl.trace) fprintf(stderr, "[ssc trace] %8.3f ms  device %d: %s\n", ms_since(pl.t_begin), d.id, what);
+	};
+	dmark("thread started");
 	size_t ev_next = 0;
 	auto new_event = [&](cudaEvent_t &e) -> int { return dc.event(ev_next++, e); };
 
@@ -667,6 +674,7 @@ int device_run(const Plan &pl, Dev &d, int phase) {
 			DCU(cudaEventRecord(up[i], dc.copy));
 		}
 		if (resident) DCU(cudaEventRecord(dc.t1, dc.copy));
+		dmark("uploads enqueued");
 		if (resident && pl.need_norm) {
 			// K4 behind the copy front, layer 0 chunk by chunk
 			for (size_t i : mine) {
@@ -688,11 +696,13 @@ int device_run(const Plan &pl, Dev &d, int phase) {
 					ssc_band hb = piece;
 					hb.out_row0 = piece.row_order == SSC_ROWS_SER ? pl.H - (pc.row0 + pc.rows) : pc.row0;
 					hb.out_rows = pc.rows;
-					DRC(ssc::launch_other_layers(hb, d.group ? nullptr : d.hist, d.group ? ssc::peer_frame_hist(d.group) : nullptr, d.flags, dc.comp),
-							"histogram launch failed");
+					uint32_t *hist = d.hist;
+					if (d.group) DRC(ssc::peer_local_histograms(d.group, pl.N, &hist, dc.comp), "histogram launch failed");
+					DRC(ssc::launch_other_layers(hb, hist, nullptr, d.flags, dc.comp), "histogram launch failed");
 				}
 			}
 			DRC(statistics_and_coefficients(pl, d, dc.comp), d.err.c_str());
+			dmark("statistics enqueued");
 		}
 		if (!resident) {	// (several pieces: the stack of this piece starts when its upload is complete)
 			DCU(cudaStreamSynchronize(dc.copy));
@@ -712,12 +722,14 @@ int device_run(const Plan &pl, Dev &d, int phase) {
 				DCU(cudaEventRecord(down[i], dc.out));
 			}
 		}
+		dmark("units enqueued");
 		if (streamed_out) {
 			for (size_t i : mine) {	// every unit's rows into the caller's image as they arrive (under the upload)
 				DCU(cudaEventSynchronize(down[i]));
 				land(pl, d.units[i].layer, d.units[i].row0, d.units[i].rows);
 			}
 		}
+		dmark("results landed");
 		DCU(cudaStreamSynchronize(dc.comp));
 		if (resident) {	// how long the upload took, and what was left to do when it ended
 			DCU(cudaStreamSynchronize(dc.copy));
@@ -765,6 +777,8 @@ int run_job(const Job &job) {
 	pl.shifted = job.op != OP_MEDIAN && job.seq->have_reg;
 	pl.plane = plane;
 	pl.cancel = &cancel;
+	pl.t_begin = t_begin;
+	pl.trace = trace;
 	{	// equally spaced host frames (one big array, as a sequence read into memory usually is): pitched copies
 		pl.strided = N > 1;
 		const char *f0 = (const char *) job.seq->frames[job.images[0]], *f1 = N > 1 ? (const char *) job.seq->frames[job.images[1]] : f0;
@@ -846,6 +860,8 @@ int run_job(const Job &job) {
 					if (cb > 0) chunk_bytes = (size_t) cb;
 				}
 				chunk = (int) std::max<size_t>(getenv("SSC_CHUNK_BYTES") ? 1 : 8, chunk_bytes / std::max<size_t>(row_bytes, 1));
+				// (a unit should still fill the GPU: at least 256 k pixels per launch however many frames there are)
+				if (!getenv("SSC_CHUNK_BYTES")) chunk = std::max(chunk, (262144 + W - 1) / W);
 				const int n_chunks = std::min(64, std::max(1, (pc.rows + chunk - 1) / chunk));
 				chunk = (pc.rows + n_chunks - 1) / n_chunks;
 			}

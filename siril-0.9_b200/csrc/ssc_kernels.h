@@ -67,7 +67,7 @@ int launch_other_layers(const ssc_band &b, uint32_t *hist, uint32_t *const *fram
 		cudaStream_t stream);
 
 // ssc_peer.cu, for the operator layer: the pieces of the exchanges it sequences itself
-uint32_t *const *peer_frame_hist(ssc_peer_group *g);	// device array: histogram pointer of every frame (at its owner)
+int peer_local_histograms(ssc_peer_group *g, int n_frames, uint32_t **hist, cudaStream_t stream);	// where this rank counts
 int peer_signal_histograms(ssc_peer_group *g, cudaStream_t stream);	// "this rank's counts are all in"
 int launch_ikss(const uint32_t *hist, int n_frames, double *stats, uint32_t *scratch, cudaStream_t stream);
 int launch_norm_coeffs(const double *stats, int n_frames, int ref_image, int mode, double *coeff,

@@ -9,12 +9,13 @@
 // operator layer).  Here every GPU ("rank") owns a block of device memory that all the others map --
 // cudaIpc handles between processes, cudaDeviceEnablePeerAccess inside one -- and the exchanges are
 // part of the kernels:
-//   K4  k_histogram flushes each frame's counts straight into the histogram of the rank that analyses
-//       that frame (frame f belongs to rank f % world): the reduce-scatter happens inside the kernel,
-//       as remote atomic adds, CTA by CTA while the others still count;
-//   K5  the owner waits for the arrival flags of all ranks, runs the IKSS on its frames, clears the
-//       histograms for the next call and stores the four statistics of each frame into every rank's
-//       table (the all-gather), then raises that rank's flag;
+//   K4  every rank counts its band into its own block and raises its flag at every rank;
+//   K5  frame f is analysed by rank f % world: that rank waits for the flags of all ranks, adds the
+//       counts of its frames straight out of the other ranks' memory (16-byte loads over NVLink: the
+//       reduce-scatter, fused into the head of the statistics pass), runs the IKSS and stores the four
+//       statistics of each frame into every rank's table (the all-gather), then raises that rank's flag;
+//       (a first version added the counts from K4's flush with remote atomics instead: 336 k four-byte
+//       atomics per rank and step ran at ~2 G/s, 0.17 ms -- slower than NCCL's reduce-scatter)
 //   K6  waits for the flags of all owners and computes the coefficients locally, identical everywhere.
 // Integer sums: the statistics stay exact under any sharding (tests/test_multirank_cpu.py for the
 // arithmetic, tests/test_gpu_operator_paths.py on two GPUs).  Flags count up monotonically (one epoch per
@@ -32,8 +33,8 @@ struct ssc_peer_group {
 	char *local = nullptr;			// this rank's block
 	char *peer[SSC_PEER_MAX] = {};		// everybody's block as mapped here (peer[rank] == local)
 	bool ipc_opened[SSC_PEER_MAX] = {};
-	uint32_t **d_frame_hist = nullptr;	// device: [n_frames_max] pointers into the owners' blocks
 	char **d_peer = nullptr;		// device: [world] block pointers
+	bool accumulating = false;		// histogram pieces of the current exchange have been counted
 	unsigned int epoch = 0;			// calls of the statistics exchange so far
 	unsigned int epoch_cnt = 0, epoch_max = 0;
 	bool connected = false;
@@ -43,7 +44,7 @@ namespace ssc {
 
 // layout of a rank's block
 struct PeerLayout {
-	size_t hist, stats, stats_own, counters, maxim, flags, status, total;
+	size_t hist_all, hist, stats, stats_own, counters, maxim, flags, status, total;
 };
 enum { FLAG_HIST = 0, FLAG_STATS = 1, FLAG_CNT = 2, FLAG_MAX = 3, N_FLAGS = 4 };
 
@@ -51,7 +52,8 @@ static PeerLayout peer_layout(int n_frames_max, int owned_max) {
 	PeerLayout l;
 	size_t o = 0;
 	auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) & ~(size_t) 255; return at; };
-	l.hist = take((size_t) owned_max * SSC_HIST_STRIDE * sizeof(uint32_t));
+	l.hist_all = take((size_t) n_frames_max * SSC_HIST_STRIDE * sizeof(uint32_t));	// this rank's band, every frame
+	l.hist = take((size_t) owned_max * SSC_HIST_STRIDE * sizeof(uint32_t));		// all bands, the frames it owns
 	l.stats = take((size_t) 4 * n_frames_max * sizeof(double));
 	l.stats_own = take((size_t) 4 * owned_max * sizeof(double));
 	l.counters = take((size_t) 2 * SSC_COUNTERS * sizeof(unsigned long long));	// two slots, by epoch parity
@@ -88,6 +90,33 @@ __global__ void k_peer_signal(char *const *peer, int world, size_t flag_offset) 
 	const int r = threadIdx.x;
 	__threadfence_system();
 	if (r < world) atomicAdd_system(reinterpret_cast<unsigned int *>(peer[r] + flag_offset), 1u);
+}
+
+// the reduce-scatter of the histograms, by the owner: slot s (frame s * world + rank) = sum over the ranks of
+// their counts of that frame, read from their blocks with 16-byte loads; every CTA first waits for all ranks
+constexpr int REDUCE_PARTS = 16;
+__global__ void __launch_bounds__(256)
+k_hist_reduce(char *const *peer, int world, int rank, int n_frames, size_t hist_all_offset, uint32_t *__restrict__ sum,
+		const unsigned int *flag, unsigned int target, int *status) {
+	__shared__ int ok;
+	if (threadIdx.x == 0) {
+		ok = wait_flag(flag, target);
+		if (!ok) atomicExch(status, SSC_PEER_TIMEOUT);
+	}
+	__syncthreads();
+	if (!ok) return;
+	const int s = blockIdx.y, f = s * world + rank;
+	if (f >= n_frames) return;
+	constexpr int VEC = SSC_HIST_STRIDE / 4;	// 65540 words = 16385 uint4
+	uint4 *dst = reinterpret_cast<uint4 *>(sum + (size_t) s * SSC_HIST_STRIDE);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < VEC; i += gridDim.x * blockDim.x) {
+		uint4 a = make_uint4(0, 0, 0, 0);
+		for (int r = 0; r < world; r++) {
+			const uint4 v = reinterpret_cast<const uint4 *>(peer[r] + hist_all_offset + (size_t) f * SSC_HIST_STRIDE * sizeof(uint32_t))[i];
+			a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+		}
+		dst[i] = a;
+	}
 }
 
 // the all-gather of the statistics: slot s of this rank is frame s * world + rank
@@ -143,11 +172,6 @@ int peer_fail(int code, const char *what, cudaError_t e = cudaSuccess) {
 PeerLayout layout_of(const ssc_peer_group *g) { return peer_layout(g->n_frames_max, g->owned_max); }
 
 int upload_tables(ssc_peer_group *g) {
-	const PeerLayout l = layout_of(g);
-	std::vector<uint32_t *> fh(g->n_frames_max);
-	for (int f = 0; f < g->n_frames_max; f++)
-		fh[f] = reinterpret_cast<uint32_t *>(g->peer[f % g->world] + l.hist) + (size_t) (f / g->world) * SSC_HIST_STRIDE;
-	PCU(cudaMemcpy(g->d_frame_hist, fh.data(), fh.size() * sizeof(uint32_t *), cudaMemcpyHostToDevice));
 	PCU(cudaMemcpy(g->d_peer, g->peer, (size_t) g->world * sizeof(char *), cudaMemcpyHostToDevice));
 	g->connected = true;
 	return SSC_OK;
@@ -155,7 +179,17 @@ int upload_tables(ssc_peer_group *g) {
 }  // namespace
 
 namespace ssc {
-uint32_t *const *peer_frame_hist(ssc_peer_group *g) { return g->d_frame_hist; }
+// this rank's own histograms of the running exchange (cleared when its first piece is counted: the owners
+// finished reading the previous exchange's before their statistics, which this rank has waited for, went out)
+int peer_local_histograms(ssc_peer_group *g, int n_frames, uint32_t **hist, cudaStream_t stream) {
+	const PeerLayout l = layout_of(g);
+	*hist = reinterpret_cast<uint32_t *>(g->local + l.hist_all);
+	if (!g->accumulating) {
+		if (cudaMemsetAsync(*hist, 0, (size_t) n_frames * SSC_HIST_STRIDE * sizeof(uint32_t), stream) != cudaSuccess) return SSC_ERR_CUDA;
+		g->accumulating = true;
+	}
+	return SSC_OK;
+}
 int peer_signal_histograms(ssc_peer_group *g, cudaStream_t stream) {
 	const PeerLayout l = layout_of(g);
 	k_peer_signal<<<1, 64, 0, stream>>>(g->d_peer, g->world, l.flags + FLAG_HIST * sizeof(unsigned int));
@@ -180,7 +214,6 @@ int ssc_peer_create(int world, int rank, int n_frames_max, ssc_peer_group **out)
 	g->bytes = l.total;
 	PCU(cudaMalloc(&g->local, l.total));		// (cudaMalloc memory: exportable through cudaIpc)
 	PCU(cudaMemset(g->local, 0, l.total));
-	PCU(cudaMalloc(&g->d_frame_hist, (size_t) n_frames_max * sizeof(uint32_t *)));
 	PCU(cudaMalloc(&g->d_peer, (size_t) world * sizeof(char *)));
 	g->peer[rank] = g->local;
 	if (world == 1) {
@@ -247,7 +280,6 @@ int ssc_peer_destroy(ssc_peer_group *g) {
 	cudaDeviceSynchronize();
 	for (int r = 0; r < g->world; r++)
 		if (g->ipc_opened[r]) cudaIpcCloseMemHandle(g->peer[r]);
-	cudaFree(g->d_frame_hist);
 	cudaFree(g->d_peer);
 	cudaFree(g->local);
 	delete g;
@@ -262,7 +294,9 @@ int ssc_dev_histogram_scatter(const ssc_band *band, ssc_peer_group *g, int last_
 	if (!band || !g || !g->connected || band->n_frames > g->n_frames_max) return peer_fail(SSC_ERR_ARG, "histogram_scatter: bad arguments");
 	const PeerLayout l = layout_of(g);
 	cudaStream_t st = (cudaStream_t) stream;
-	int rc = launch_histogram_to(*band, nullptr, g->d_frame_hist, st);
+	uint32_t *hist = nullptr;
+	int rc = peer_local_histograms(g, band->n_frames, &hist, st);
+	if (!rc) rc = launch_histogram(*band, hist, st);
 	if (rc) return peer_fail(rc, "histogram launch failed");
 	if (!last_piece) return SSC_OK;	// more row pieces of this rank's band follow: one arrival flag per call of the exchange
 	k_peer_signal<<<1, 64, 0, st>>>(g->d_peer, g->world, l.flags + FLAG_HIST * sizeof(unsigned int));
@@ -282,12 +316,15 @@ int ssc_dev_ikss_gather(ssc_peer_group *g, int n_frames, uint32_t *scratch, void
 	uint32_t *hist = reinterpret_cast<uint32_t *>(g->local + l.hist);
 	double *own = reinterpret_cast<double *>(g->local + l.stats_own);
 	int *status = reinterpret_cast<int *>(g->local + l.status);
-	k_peer_wait<<<1, 1, 0, st>>>(reinterpret_cast<unsigned int *>(g->local + l.flags) + FLAG_HIST, g->epoch * (unsigned int) g->world, status);
+	g->accumulating = false;
 	if (owned > 0) {
+		dim3 grid(REDUCE_PARTS, owned);
+		k_hist_reduce<<<grid, 256, 0, st>>>(g->d_peer, g->world, g->rank, n_frames, l.hist_all, hist,
+				reinterpret_cast<unsigned int *>(g->local + l.flags) + FLAG_HIST, g->epoch * (unsigned int) g->world, status);
 		int rc = launch_ikss(hist, owned, own, scratch, st);
 		if (rc) return peer_fail(rc, "ikss launch failed");
-		// the histograms start the next call empty; nobody adds to them before this rank's flag below has moved
-		PCU(cudaMemsetAsync(hist, 0, (size_t) owned * SSC_HIST_STRIDE * sizeof(uint32_t), st));
+	} else {
+		k_peer_wait<<<1, 1, 0, st>>>(reinterpret_cast<unsigned int *>(g->local + l.flags) + FLAG_HIST, g->epoch * (unsigned int) g->world, status);
 	}
 	k_stats_scatter<<<g->world, 128, 0, st>>>(g->d_peer, g->world, g->rank, n_frames, owned > 0 ? owned : 1, own, l.stats,
 			l.flags + FLAG_STATS * sizeof(unsigned int));
