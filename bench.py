@@ -446,6 +446,14 @@ def main():
                 r = e2e_step()
             e2e_ms = (time.perf_counter() - t_wall0) * 1e3 / max(e2e_steps, 1)
             pkg.set_devices([0])
+        # the other ranks wait on the HOST (the store): a NCCL barrier would spin a kernel on their GPUs and time-slice
+        # with the kernels rank 0 runs there
+        if world > 1:
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                store.set("ssc_e2e_done", "1")
+            else:
+                store.wait(["ssc_e2e_done"])
         sync_all()
         e2e_parity, op_timing = None, None
         if rank == 0 and r is not None:

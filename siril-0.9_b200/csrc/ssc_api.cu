@@ -544,7 +544,7 @@ int statistics_and_coefficients(const Plan &pl, Dev &d, cudaStream_t st) {
 }
 
 // one unit through its kernel (everything but stack_summing's second pass)
-int launch_unit(const Plan &pl, Dev &d, const ssc_band &piece, const Piece &pc, const Unit &u, cudaStream_t st) {
+int launch_unit(const Plan &pl, Dev &d, const ssc_band &piece, const Piece &pc, const Unit &u, int hb_defer, cudaStream_t st) {
 	const Job &job = *pl.job;
 	ssc_band ub;
 	unit_band(piece, u, ub);
@@ -565,6 +565,11 @@ int launch_unit(const Plan &pl, Dev &d, const ssc_band &piece, const Piece &pc, 
 	p.out_layer_stride = layer_out;
 	p.out_buf_row0 = pc.row0;
 	p.counters = d.counters + (size_t) u.layer * SSC_COUNTERS;	// the kernel sees layer 0: one counter set per layer
+	p.hb_defer = hb_defer;		// (linear fit: undecided pixels are listed in the piece's geometry and finished once)
+	p.hb_layer0 = u.layer;
+	p.hb_row0 = u.row0 - pc.row0;
+	p.hb_rows = pc.rows;
+	p.hb_pixels = (unsigned long long) pl.C * pc.rows * pl.W;
 	return ssc::launch_stack(p, job.op == OP_MEDIAN, st);
 }
 
@@ -708,11 +713,27 @@ int device_run(const Plan &pl, Dev &d, int phase) {
 			DCU(cudaStreamSynchronize(dc.copy));
 			d.t_h2d += ms_since(t_up);
 		}
-		const bool streamed_out = job.op != OP_SUM;	// stack_summing writes after the global maximum is known
+		// Linear fit through the warp kernel: the few pixels its screening cannot decide go through gsl_fit_linear's
+		// literal recurrences, ~8 ms per launch however few they are -- listed by every unit, finished once per piece,
+		// and the piece's rows go down after that
+		bool defer = false;
+		if (job.op == OP_MEAN && job.rejection == LINEARFIT && ssc::g_kernel_path != 1 && !mine.empty()) {
+			ssc::StackParams probe{};
+			unit_band(piece, d.units[mine[0]], probe.band);
+			probe.rejection = LINEARFIT;
+			probe.out = d.out;
+			probe.out_layer_stride = (size_t) pc.rows * pl.W;
+			defer = ssc::warp_path_eligible(probe, 0);
+		}
+		const bool streamed_out = job.op != OP_SUM && !defer;	// stack_summing writes after the global maximum is known
+		std::vector<cudaEvent_t> tk0, tk1;		// SSC_TRACE: when every unit's kernels ran
+		const bool unit_trace = pl.trace && resident;	// (dc.t0: the moment the first upload began)
 		for (size_t i : mine) {
 			const Unit &u = d.units[i];
 			DCU(cudaStreamWaitEvent(dc.comp, up[i], 0));
-			DRC(launch_unit(pl, d, piece, pc, u, dc.comp), "stack launch failed");
+			if (unit_trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, dc.comp); tk0.push_back(e); }
+			DRC(launch_unit(pl, d, piece, pc, u, defer ? (i == mine[0] ? 2 : 1) : 0, dc.comp), "stack launch failed");
+			if (unit_trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, dc.comp); tk1.push_back(e); }
 			if (streamed_out) {
 				DRC(new_event(done[i]), "event");
 				DCU(cudaEventRecord(done[i], dc.comp));
@@ -722,6 +743,21 @@ int device_run(const Plan &pl, Dev &d, int phase) {
 				DCU(cudaEventRecord(down[i], dc.out));
 			}
 		}
+		if (defer) {
+			ssc::StackParams p{};
+			p.band = piece;
+			p.normalize = job.normalize;
+			p.coeff = pl.need_norm ? d.coeff : nullptr;
+			p.rejection = job.rejection;
+			p.sig_low = job.sig[0];
+			p.sig_high = job.sig[1];
+			p.out = d.out;
+			p.out_layer_stride = (size_t) pc.rows * pl.W;
+			p.out_buf_row0 = pc.row0;
+			p.counters = d.counters;	// real layer numbers here: layer c's counts land in set 0, slots 2 c and 2 c + 1
+			DRC(ssc::launch_deferred_handback(p, dc.comp), "hand-back launch failed");
+			for (int c = 0; c < pl.C; c++) DRC(download_rows(pl, d, pc, c, pc.row0, pc.rows, dc.comp), "download failed");
+		}
 		dmark("units enqueued");
 		if (streamed_out) {
 			for (size_t i : mine) {	// every unit's rows into the caller's image as they arrive (under the upload)
@@ -729,8 +765,19 @@ int device_run(const Plan &pl, Dev &d, int phase) {
 				land(pl, d.units[i].layer, d.units[i].row0, d.units[i].rows);
 			}
 		}
-		dmark("results landed");
 		DCU(cudaStreamSynchronize(dc.comp));
+		if (defer) for (int c = 0; c < pl.C; c++) land(pl, c, pc.row0, pc.rows);
+		dmark("results landed");
+		if (unit_trace) {
+			for (size_t k = 0; k < tk0.size(); k++) {
+				float a = 0, b = 0;
+				cudaEventElapsedTime(&a, dc.t0, tk0[k]);
+				cudaEventElapsedTime(&b, tk0[k], tk1[k]);
+				fprintf(stderr, "[ssc trace]   device %d unit %zu (layer %d rows %d+%d): kernels start %.3f ms after the first upload began, run %.3f ms\n",
+						d.id, k, d.units[mine[k]].layer, d.units[mine[k]].row0, d.units[mine[k]].rows, a, b);
+				cudaEventDestroy(tk0[k]); cudaEventDestroy(tk1[k]);
+			}
+		}
 		if (resident) {	// how long the upload took, and what was left to do when it ended
 			DCU(cudaStreamSynchronize(dc.copy));
 			float ms = 0.0f;
@@ -1067,9 +1114,10 @@ int run_job(const Job &job) {
 		CU(cudaSetDevice(d.id));
 		CU(cudaMemcpy(h_cnt, d.counters, sizeof(h_cnt), cudaMemcpyDeviceToHost));
 		if (job.op == OP_MEAN) {
-			for (int c = 0; c < C; c++) {	// one counter set per layer (every unit's kernel saw a single layer)
-				res.irej[c][0] += h_cnt[c * SSC_COUNTERS + 0];
-				res.irej[c][1] += h_cnt[c * SSC_COUNTERS + 1];
+			for (int c = 0; c < C; c++) {	// one counter set per layer (every unit's kernel saw a single layer);
+				// a deferred hand-back pass knows the real layers and counts layer c in set 0, slots 2 c and 2 c + 1
+				res.irej[c][0] += h_cnt[c * SSC_COUNTERS + 0] + (c > 0 ? h_cnt[2 * c + 0] : 0);
+				res.irej[c][1] += h_cnt[c * SSC_COUNTERS + 1] + (c > 0 ? h_cnt[2 * c + 1] : 0);
 				res.guard_fired += h_cnt[c * SSC_COUNTERS + 6];
 				res.cap_hit += h_cnt[c * SSC_COUNTERS + 7];
 			}

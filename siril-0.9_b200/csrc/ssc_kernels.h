@@ -31,6 +31,13 @@ struct StackParams {
 	int out_buf_row0;
 	unsigned long long *counters;	// device uint64[SSC_COUNTERS] or nullptr
 	FitTables fit;			// filled by launch_stack() for LINEARFIT
+	// Deferred hand-back (the operator layer stacks a band unit by unit): 0 = every launch finishes its own
+	// undecided pixels; 1 / 2 = the warp kernel only lists them (2: the list starts empty), with pixel ids in the
+	// geometry of the whole piece (layer + hb_layer0, row + hb_row0 of hb_rows rows, hb_pixels in all), and
+	// launch_deferred_handback() finishes the whole list once -- the literal fit costs ~8 ms per launch however few
+	// pixels it gets
+	int hb_defer, hb_layer0, hb_row0, hb_rows;
+	unsigned long long hb_pixels;
 };
 
 // ssc_stack_generic.cu
@@ -46,6 +53,8 @@ int launch_stack_mid(const StackParams &p, int is_median, cudaStream_t stream);
 // ssc_stack_warp.cu: one warp per pixel pair -- linear fit (8..1024 frames), median of 513..1024 frames
 bool warp_path_eligible(const StackParams &p, int is_median);
 int launch_stack_warp(const StackParams &p, int is_median, cudaStream_t stream);
+// finishes what launches with hb_defer listed; p describes the whole piece (its band, result and counters)
+int launch_deferred_handback(const StackParams &p, cudaStream_t stream);
 // picks the register-network kernel when the shape allows it, the general kernel otherwise
 int launch_stack(const StackParams &p, int is_median, cudaStream_t stream);
 void release_kernel_scratch(int dev);	// per-device lists and tables the kernels keep between launches

@@ -40,20 +40,21 @@ struct LeftoverIdStore {
 };
 inline LeftoverIdStore g_leftover_id_store[64];
 
-inline int leftover_ids(unsigned long long pixels, LeftoverList &list, cudaStream_t stream) {
+inline int leftover_ids(unsigned long long pixels, LeftoverList &list, cudaStream_t stream, bool keep_items = false) {
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev < 0 || dev >= 64 || pixels > 0xFFFFFFF0ull) return SSC_ERR_ARG;
 	LeftoverIdStore &st = g_leftover_id_store[dev];
 	if (!st.count && cudaMalloc(&st.count, 2 * sizeof(unsigned int)) != cudaSuccess) return SSC_ERR_CUDA;
 	if (st.capacity < pixels) {
+		if (keep_items) return SSC_ERR_ARG;	// (the deferred list is sized by its first launch)
 		if (st.ids) cudaFree(st.ids);
 		st.ids = nullptr;
 		st.capacity = 0;
 		if (cudaMalloc(&st.ids, (size_t) pixels * sizeof(unsigned int)) != cudaSuccess) return SSC_ERR_CUDA;
 		st.capacity = (size_t) pixels;
 	}
-	if (cudaMemsetAsync(st.count, 0, 2 * sizeof(unsigned int), stream) != cudaSuccess) return SSC_ERR_CUDA;
+	if (cudaMemsetAsync(keep_items ? st.count + 1 : st.count, 0, (keep_items ? 1 : 2) * sizeof(unsigned int), stream) != cudaSuccess) return SSC_ERR_CUDA;
 	list.count = st.count;
 	list.capacity = (unsigned int) pixels;
 	list.ids = st.ids;

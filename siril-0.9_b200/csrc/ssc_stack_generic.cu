@@ -239,6 +239,21 @@ static int launch_stack_unchained(const StackParams &p_in, int is_median, cudaSt
 	return launch_stack_generic(p, nullptr, nullptr, 0, is_median, stream);
 }
 
+// what launches with hb_defer listed (ssc_stack_warp.cu), finished in one go: p is the whole piece
+int launch_deferred_handback(const StackParams &p_in, cudaStream_t stream) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) return SSC_ERR_ARG;
+	const LeftoverIdStore &st = g_leftover_id_store[dev];
+	if (!st.count || !st.ids) return SSC_OK;	// nothing was ever listed on this device
+	StackParams p = p_in;
+	p.hb_defer = 0;
+	int rc = fit_tables(p.fit, stream);
+	if (rc) return rc;
+	const unsigned long long pixels = (unsigned long long) p.band.layers * p.band.out_rows * p.band.width;
+	return launch_stack_generic(p, st.ids, st.count, (unsigned int) (pixels < st.capacity ? pixels : st.capacity), 0, stream);
+}
+
 int launch_stack(const StackParams &p, int is_median, cudaStream_t stream) {
 	int dev = 0;
 	cudaGetDevice(&dev);

@@ -25,6 +25,7 @@
 //      (ssc_column.cuh), so no result ever depends on the screening arithmetic;
 //   4. the reference's `if (N - r <= 4) break;` (stacking.c:1771) is applied from prefix counts of the
 //      flags: the samples behind the break keep flag 0, the event is counted (guard_fired).
+#include <algorithm>
 #include "ssc_column.cuh"
 #include "ssc_kernels.h"
 #include "ssc_leftover.cuh"
@@ -313,7 +314,8 @@ k_stack_warp(StackParams p, unsigned int n_pairs, int is_median, LeftoverList li
 				} else {
 					const unsigned int slot = atomicAdd(list.count, 1u);
 					if (slot < list.capacity)
-						list.ids[slot] = (unsigned int) (((size_t) layer * b.out_rows + rr) * W + 2 * x2 + sel);
+						list.ids[slot] = (unsigned int) (((size_t) (layer + p.hb_layer0) * (p.hb_defer ? p.hb_rows : b.out_rows)
+								+ rr + p.hb_row0) * W + 2 * x2 + sel);
 				}
 			}
 		}
@@ -348,9 +350,10 @@ static int launch_warp(const StackParams &p, int is_median, cudaStream_t stream)
 	if (cudaFuncSetAttribute(k_stack_warp<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
 	LeftoverList list{nullptr, 0, nullptr, nullptr};
-	const unsigned long long pixels = (unsigned long long) b.layers * b.out_rows * b.width;
+	const unsigned long long pixels = p.hb_defer ? p.hb_pixels : (unsigned long long) b.layers * b.out_rows * b.width;
+	if (pixels >= 0xFFFFFFF0ull) return SSC_ERR_ARG;
 	if (!is_median) {
-		int rc = leftover_ids(pixels, list, stream);
+		int rc = leftover_ids(pixels, list, stream, p.hb_defer == 1);
 		if (rc) return rc;
 	}
 	int dev = 0, sms = 148, per_sm = 1;
@@ -363,7 +366,7 @@ static int launch_warp(const StackParams &p, int is_median, cudaStream_t stream)
 	if (blocks > need) blocks = need;
 	k_stack_warp<R><<<(unsigned int) blocks, 32 * WARP_PAIRS, smem, stream>>>(p, (unsigned int) pairs, is_median, list);
 	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
-	if (!is_median)	// pixels the screening could not decide: gsl_fit_linear's literal recurrences (ssc_column.cuh)
+	if (!is_median && !p.hb_defer)	// pixels the screening could not decide: gsl_fit_linear's literal recurrences (ssc_column.cuh)
 		return launch_stack_generic(p, list.ids, list.count, (unsigned int) pixels, 0, stream);
 	return SSC_OK;
 }
