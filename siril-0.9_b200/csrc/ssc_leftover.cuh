@@ -40,6 +40,8 @@ struct LeftoverIdStore {
 };
 inline LeftoverIdStore g_leftover_id_store[64];
 
+int launch_fit_handback(const StackParams &p, const LeftoverList &list, cudaStream_t stream);	// ssc_stack_warp.cu
+
 inline int leftover_ids(unsigned long long pixels, LeftoverList &list, cudaStream_t stream, bool keep_items = false) {
 	int dev = 0;
 	cudaGetDevice(&dev);

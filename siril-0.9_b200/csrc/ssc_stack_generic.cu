@@ -251,7 +251,8 @@ int launch_deferred_handback(const StackParams &p_in, cudaStream_t stream) {
 	int rc = fit_tables(p.fit, stream);
 	if (rc) return rc;
 	const unsigned long long pixels = (unsigned long long) p.band.layers * p.band.out_rows * p.band.width;
-	return launch_stack_generic(p, st.ids, st.count, (unsigned int) (pixels < st.capacity ? pixels : st.capacity), 0, stream);
+	LeftoverList list{st.count, (unsigned int) (pixels < st.capacity ? pixels : st.capacity), st.ids, st.count + 1};
+	return launch_fit_handback(p, list, stream);
 }
 
 int launch_stack(const StackParams &p, int is_median, cudaStream_t stream) {

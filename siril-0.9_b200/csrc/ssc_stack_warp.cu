@@ -326,6 +326,86 @@ k_stack_warp(StackParams p, unsigned int n_pairs, int is_median, LeftoverList li
 			if (cnt[k]) atomicAdd(&p.counters[k], cnt[k]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The pixels the screening could not decide (an exact tie of a residual with a threshold, a vanishing sigma):
+// one warp per listed pixel reloads and sorts the column the same way, then lane 0 runs the complete
+// LINEARFIT of ssc_column.cuh -- gsl_fit_linear's literal running means -- on a shared-memory copy.  (The general
+// kernel's list mode did this with a serial shared-memory bitonic sort per thread: ~8 ms per launch for 1000
+// frames however few pixels were listed.)
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(32 * WARP_PAIRS)
+k_fit_handback(StackParams p, LeftoverList list) {
+	extern __shared__ __align__(16) WORD s_cols[];		// [warps][32 R] the pixel's sorted column
+	const ssc_band &b = p.band;
+	const int W = b.width, N = b.n_frames, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
+	WORD *col = s_cols + (size_t) warp * 32 * R;
+	unsigned int n_items = *list.count;
+	if (n_items > list.capacity) n_items = list.capacity;
+	for (unsigned int item = blockIdx.x * WARP_PAIRS + warp; item < n_items; item += gridDim.x * WARP_PAIRS) {
+		const unsigned int pix = list.ids[item];
+		const unsigned int row = pix / (unsigned int) W;
+		const int x = (int) (pix - row * (unsigned int) W);
+		const int layer = (int) (row / (unsigned int) b.out_rows);
+		const int rr = (int) (row - (unsigned int) layer * (unsigned int) b.out_rows);
+		const int Rr = b.out_row0 + rr;
+		const int srow = b.row_order == SSC_ROWS_SER ? b.height - 1 - Rr : Rr;
+		const WORD *src = b.frames + (size_t) layer * b.layer_stride + (size_t) (srow - b.buf_row0) * W + x;
+		unsigned int v[R], sum = 0;
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			const int f = r * 32 + lane;
+			unsigned int s = 0xFFFFu;				// sentinels sort behind the samples
+			if (f < N) {
+				s = __ldg(src + (size_t) f * b.frame_stride);
+				if (norm) s = normalize_sample(s, p.normalize, p.coeff[f], p.coeff[N + f], p.coeff[2 * N + f]);
+				sum += s;
+			}
+			v[r] = s;						// (the upper halves stay 0 through the packed min / max)
+		}
+		warp_sort<R>(v, lane);
+#pragma unroll
+		for (int r = 0; r < R; r++) col[lane * R + r] = (WORD) v[r];
+		const unsigned long long S = (unsigned long long) (unsigned int) warp_sum((int) sum);
+		__syncwarp();
+		if (lane == 0) {
+			RejectState st{0, 0, 0, 0};
+			const unsigned int res = reject_sorted_and_mean<false>(Column{col, 1}, N, LINEARFIT, p.sig_low, p.sig_high, S, 0ull, st,
+					nullptr, &p.fit);
+			p.out[(size_t) layer * p.out_layer_stride + (size_t) (Rr - p.out_buf_row0) * W + x] = (WORD) res;
+			if (p.counters) {
+				if (st.rej_lo) atomicAdd(&p.counters[layer * 2 + 0], (unsigned long long) st.rej_lo);
+				if (st.rej_hi) atomicAdd(&p.counters[layer * 2 + 1], (unsigned long long) st.rej_hi);
+				if (st.guard) atomicAdd(&p.counters[6], 1ull);
+				if (st.cap) atomicAdd(&p.counters[7], 1ull);
+			}
+		}
+		__syncwarp();
+	}
+}
+
+template <int R>
+static int launch_fit_handback_r(const StackParams &p, const LeftoverList &list, cudaStream_t stream) {
+	const size_t smem = (size_t) WARP_PAIRS * 32 * R * sizeof(WORD);
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	k_fit_handback<R><<<sms * 2, 32 * WARP_PAIRS, smem, stream>>>(p, list);
+	return cudaGetLastError() == cudaSuccess ? SSC_OK : SSC_ERR_CUDA;
+}
+
+// p.fit must hold the tables (launch_stack / launch_deferred_handback fill them)
+int launch_fit_handback(const StackParams &p, const LeftoverList &list, cudaStream_t stream) {
+	const int n = p.band.n_frames;
+	if (n <= 32) return launch_fit_handback_r<1>(p, list, stream);
+	if (n <= 64) return launch_fit_handback_r<2>(p, list, stream);
+	if (n <= 128) return launch_fit_handback_r<4>(p, list, stream);
+	if (n <= 256) return launch_fit_handback_r<8>(p, list, stream);
+	if (n <= 512) return launch_fit_handback_r<16>(p, list, stream);
+	return launch_fit_handback_r<32>(p, list, stream);
+}
+
 // Same shape conditions as the other packed-pair kernels; linear fit from 8 frames on (fewer: the
 // general kernel), the median above 512 frames (below, ssc_stack_fast.cu / ssc_stack_mid.cu are the
 // better sorters).
@@ -367,7 +447,7 @@ static int launch_warp(const StackParams &p, int is_median, cudaStream_t stream)
 	k_stack_warp<R><<<(unsigned int) blocks, 32 * WARP_PAIRS, smem, stream>>>(p, (unsigned int) pairs, is_median, list);
 	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
 	if (!is_median && !p.hb_defer)	// pixels the screening could not decide: gsl_fit_linear's literal recurrences (ssc_column.cuh)
-		return launch_stack_generic(p, list.ids, list.count, (unsigned int) pixels, 0, stream);
+		return launch_fit_handback(p, list, stream);
 	return SSC_OK;
 }
 
