@@ -87,3 +87,61 @@ def test_sharded_equals_unsharded(tmp_path, world):
         assert np.array_equal(z["irej"].reshape(3, 2), whole["irej"].astype(np.int64))
         got[:, int(z["row0"]):int(z["row0"]) + int(z["rows"]), :] = z["out"]
     assert np.array_equal(got, whole["out"])
+
+
+def _worker_owners(rank, world, port_no, tmpdir):
+    """The peer-group protocol of csrc/ssc_peer.cu restated on gloo: every rank counts its band, frame f is
+    analysed by rank f % world from the sum of all ranks' counts (slot s of a rank is frame s * world + rank),
+    the four statistics per frame are gathered on every rank."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import synth
+    from oracle import port
+    bench = _bench_module()
+    n, c, h, w = 7, 1, 29, 40                                           # 7 frames: not a multiple of 2 or 3
+    frames = synth.make_frames(n, c, h, w, seed=9, outlier_p=5e-3, zero_p=2e-3, stars=3)
+    row0, rows = bench.band_rows(h, world, rank)
+    band = np.ascontiguousarray(frames[:, :, row0:row0 + rows, :])
+    mine = torch.from_numpy(np.stack([port.histogram(f)[0] for f in band]).astype(np.int64))
+    everyone = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(everyone, mine)                                     # (the kernels read the peers' blocks instead)
+    owned = (n - rank + world - 1) // world
+    own_stats = torch.zeros((4, max(owned, 1)), dtype=torch.float64)
+    for s in range(owned):
+        f = s * world + rank
+        hk = sum(e[f] for e in everyone).numpy().astype(np.uint32)
+        hk[0] = 0
+        loc, sc, _ = port.ikss_hist(hk)
+        own_stats[:, s] = torch.tensor([loc, sc, 65535.0, float(hk.sum())], dtype=torch.float64)
+    pad = torch.zeros((4, (n + world - 1) // world), dtype=torch.float64)
+    pad[:, :own_stats.shape[1]] = own_stats[:, :pad.shape[1]]
+    table = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(table, pad)
+    stats = np.zeros((4, n))
+    for r in range(world):
+        for s in range(pad.shape[1]):
+            if s * world + r < n:
+                stats[:, s * world + r] = table[r][:, s].numpy()
+    coeff = port.norm_coeffs(port.ADDITIVE_SCALING, stats[0], stats[1])
+    np.savez(os.path.join(tmpdir, "own%d.npz" % rank), coeff=coeff, stats=stats)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_frame_owners_protocol(tmp_path, world):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port_no = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker_owners, args=(world, port_no, str(tmp_path)), nprocs=world, join=True)
+    import synth
+    from oracle import port
+    frames = synth.make_frames(7, 1, 29, 40, seed=9, outlier_p=5e-3, zero_p=2e-3, stars=3)
+    st = [port.frame_stats_hist(f) for f in frames]
+    coeff = port.norm_coeffs(port.ADDITIVE_SCALING, [x[0] for x in st], [x[1] for x in st])
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), "own%d.npz" % r))
+        assert np.array_equal(z["coeff"], coeff)                        # every rank, bit for bit
+        assert np.array_equal(z["stats"][0], [x[0] for x in st]) and np.array_equal(z["stats"][1], [x[1] for x in st])
