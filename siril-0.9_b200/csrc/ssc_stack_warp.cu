@@ -265,16 +265,23 @@ k_stack_warp(StackParams p, unsigned int n_pairs, int is_median, LeftoverList li
 			const int f = r * 32 + lane;
 			v[r] = f < N ? __ldg(reinterpret_cast<const unsigned int *>(src + (unsigned long long) f * fstride)) : 0xFFFFFFFFu;
 		}
-		if (norm) {	// normalization (stacking.c:1635-1652, :750-764), the conversion-based exact form
+		if (norm) {	// normalization (stacking.c:1635-1652, :750-764), the conversion-based exact form: a ROLLED loop over
+			// a shared-memory copy of the column (unrolled per register it was 7 k instructions of a 13 k kernel,
+			// and instruction fetch stalled every launch whether it normalized or not)
+			unsigned int *s_w = reinterpret_cast<unsigned int *>(s_fit) + (size_t) warp * 32 * R * 2;	// the warp's fit area
 #pragma unroll
-			for (int r = 0; r < R; r++) {
-				const int f = r * 32 + lane;
-				if (f < N) {
-					const double off = p.coeff[f], mul = p.coeff[N + f], sc = p.coeff[2 * N + f];
-					v[r] = normalize_sample(v[r] & 0xFFFFu, p.normalize, off, mul, sc)
-							| (normalize_sample(v[r] >> 16, p.normalize, off, mul, sc) << 16);
-				}
+			for (int r = 0; r < R; r++) s_w[r * 32 + lane] = v[r];
+			__syncwarp();
+#pragma unroll 1
+			for (int f = lane; f < N; f += 32) {
+				const unsigned int w = s_w[f];
+				const double off = p.coeff[f], mul = p.coeff[N + f], sc = p.coeff[2 * N + f];
+				s_w[f] = normalize_sample(w & 0xFFFFu, p.normalize, off, mul, sc) | (normalize_sample(w >> 16, p.normalize, off, mul, sc) << 16);
 			}
+			__syncwarp();
+#pragma unroll
+			for (int r = 0; r < R; r++) v[r] = s_w[r * 32 + lane];
+			__syncwarp();
 		}
 
 		// ---- 2. sort: lane l ends up with sorted samples [l R, (l + 1) R) of both pixels ----
@@ -426,7 +433,8 @@ static int launch_warp(const StackParams &p, int is_median, cudaStream_t stream)
 	const unsigned long long pairs = (unsigned long long) (b.width >> 1) * b.layers * b.out_rows;
 	if (pairs == 0) return SSC_OK;
 	if (pairs >= 0xFFFFFFF0ull) return SSC_ERR_ARG;
-	const size_t smem = is_median ? 0 : (size_t) WARP_PAIRS * 32 * R * sizeof(double);
+	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
+	const size_t smem = (is_median && !norm) ? 0 : (size_t) WARP_PAIRS * 32 * R * sizeof(double);	// the fit's doubles / the normalization's copy
 	if (cudaFuncSetAttribute(k_stack_warp<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
 	LeftoverList list{nullptr, 0, nullptr, nullptr};
