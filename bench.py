@@ -41,7 +41,11 @@ L2_BYTES = 126 << 20
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel's launch over the whole
 # image on one GPU, from one `ncu --set full` capture each (profiles/): None where not captured
 DRAM_BYTES_N1 = {
-    "cfg3": (9_252_995_000 + 163_980_288, "profiles/r01_ncu_k_stack_fast_full_size_launch.txt"),
+    "cfg1": (33_564_928, "profiles/r02_ncu_cfg1_sum.txt (k_sum_rows_vec8, whole image)"),
+    "cfg2": (1_074_024_000 + 34_832_896, "profiles/r02_ncu_cfg2_median.txt (whole image)"),
+    "cfg3": (9_252_995_000 + 163_980_288, "profiles/r01_ncu_k_stack_fast_full_size_launch.txt (whole image)"),
+    "cfg4": (8 * (821_562_880 + 37_642_752), "profiles/r02_ncu_cfg4_mid.txt (440-row slice = 1/8 of the image, x 8)"),
+    "cfg5": (8 * (692_242_432 + 12_340_992), "profiles/r02_ncu_cfg5_warp_final.txt (152-row slice = 1/8 of the image, x 8)"),
 }
 DOMINANT = {
     "cfg1": "k_sum_rows_vec8 (K1: per-pixel u32 sums + max)",
@@ -546,7 +550,8 @@ def main():
                             "inputs (%.0f MB) fit L2: a 256 MB buffer is written between timed steps (outside the per-step events)" % (in_bytes / world / 1e6)),
                         seed=hex(SEED), rejection_counters=irej.tolist(), guard_fired=guard, cap_hit=cap),
             roofline=dict(bound="hbm", kernel=DOMINANT[key], achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                          traffic=(traffic // world) if traffic else None, traffic_source=traffic_src,
+                          traffic=(traffic // world) if traffic else None,
+                          traffic_source=("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture: %s; / ranks" % traffic_src) if traffic else None,
                           peak_source=peak_src, algorithmic_bytes_per_launch=kernel_bytes, ms_per_launch=kernel_ms),
             step_breakdown_ms=breakdown,
             step_hbm_frac=(full_stack + full_stats) / world / (ms_step / 1e3) / 1e9 / peak,
