@@ -210,7 +210,9 @@ int ssc_release_workspace(void);
 int ssc_set_devices(const int *device_ids, int count);
 int ssc_device_count(void);
 /* Diagnostic: 0 = pick the kernel by shape (default), 1 = always use the general
- * shared-memory kernel.  Both give identical results (tests/test_gpu_parity.py). */
+ * shared-memory kernel, 2 = pick by shape but never use the one-FMA form of the
+ * normalization (which is otherwise used on launches whose coefficients it was verified
+ * for, sample value by sample value).  All give identical results (tests/test_gpu_parity.py). */
 int ssc_set_kernel_path(int mode);
 const char *ssc_last_error(void);
 const char *ssc_version(void);

@@ -214,7 +214,7 @@ def device_count():
 
 
 def set_kernel_path(mode):
-    """0 = automatic kernel choice, 1 = general kernel only (diagnostic)."""
+    """0 = automatic kernel choice, 1 = general kernel only, 2 = automatic with the exact normalization only (diagnostic)."""
     rc = _lib.ssc_set_kernel_path(int(mode))
     if rc:
         raise StackError(rc, "ssc_set_kernel_path")

@@ -97,7 +97,7 @@ const char *ssc_last_error(void) { return g_err.c_str(); }
 const char *ssc_version(void) { return "siril-stack-cuda 0.1 (sm_100a)"; }
 
 int ssc_set_kernel_path(int mode) {
-	if (mode < 0 || mode > 1) return fail(SSC_ERR_ARG, "kernel path must be 0 (automatic) or 1 (general kernel only)");
+	if (mode < 0 || mode > 2) return fail(SSC_ERR_ARG, "kernel path must be 0 (automatic), 1 (general kernel only) or 2 (automatic, exact normalization only)");
 	ssc::g_kernel_path = mode;
 	return SSC_OK;
 }

@@ -24,6 +24,10 @@ struct StackParams {
 	ssc_band band;
 	int normalize;
 	const double *coeff;		// device double[3][N] or nullptr
+	// device uint[N] written by k_verify_cheap_norm, or nullptr: norm_bad[f] == 0 means that the cheap form of the
+	// normalization (ssc_network.cuh) equals the reference's for every sample value of frame f.  Filled in by
+	// launch_stack() -- callers leave it alone.
+	const unsigned int *norm_bad;
 	int rejection;
 	double sig_low, sig_high;
 	WORD *out;
@@ -58,7 +62,7 @@ int launch_deferred_handback(const StackParams &p, cudaStream_t stream);
 // picks the register-network kernel when the shape allows it, the general kernel otherwise
 int launch_stack(const StackParams &p, int is_median, cudaStream_t stream);
 void release_kernel_scratch(int dev);	// per-device lists and tables the kernels keep between launches
-extern int g_kernel_path;	// 0 automatic, 1 general kernel only (ssc_set_kernel_path)
+extern int g_kernel_path;	// 0 automatic, 1 general kernel only, 2 automatic without the cheap normalization (ssc_set_kernel_path)
 
 // ssc_sum.cu
 int launch_extreme(const ssc_band &b, bool take_max, WORD *out, unsigned int *extreme, cudaStream_t stream);

@@ -14,6 +14,8 @@
 #include "ssc_kernels.h"
 #include <mutex>
 #include "ssc_leftover.cuh"
+#include "ssc_network.cuh"
+#include <cstdlib>
 
 namespace ssc {
 
@@ -197,10 +199,52 @@ static int fit_tables(FitTables &fit, cudaStream_t stream) {
 	return SSC_OK;
 }
 
+// ---------------------------------------------------------------------------
+// The cheap form of the normalization (ssc_network.cuh) is only used on frames for which it has been
+// compared with the reference's form, normalize_sample(), on ALL 65536 sample values: one CTA per frame,
+// bad[f] = 1 if any value differs (or the coefficients leave the 2^52 forms' domain).  ~3 us per launch.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_verify_cheap_norm(const double *__restrict__ coeff, int n, int mode, unsigned int *__restrict__ bad) {
+	const int f = blockIdx.x;
+	const double off = coeff[f], mul = coeff[n + f], sc = coeff[2 * n + f];
+	int differs = !norm_domain_ok(mode, off, mul, sc);
+	if (!differs) {
+		for (unsigned int v = threadIdx.x; v < 65536u; v += 256u) {
+			bool hi_ok;
+			differs |= cheap_sample_dyn(v, mode, off, mul, sc, hi_ok) != normalize_sample(v, mode, off, mul, sc);
+			differs |= !hi_ok;
+		}
+	}
+	differs = __syncthreads_or(differs);
+	if (threadIdx.x == 0) bad[f] = differs ? 1u : 0u;
+}
+
+static unsigned int *g_norm_bad_store[64];	// per device: [SSC_GENERIC_MAX_FRAMES]
+
+// verifies the launch's coefficients on its stream; p.norm_bad stays nullptr (exact form) when switched off
+static int verify_cheap_norm(StackParams &p, cudaStream_t stream) {
+	static int enabled = -1;
+	if (enabled < 0) { const char *e = getenv("SSC_CHEAP_NORM"); enabled = e ? atoi(e) != 0 : 1; }
+	p.norm_bad = nullptr;
+	const int n = p.band.n_frames;
+	if (!enabled || g_kernel_path == 2 || !p.coeff || p.normalize == NO_NORM || n < 1 || n > SSC_GENERIC_MAX_FRAMES) return SSC_OK;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) return SSC_ERR_ARG;
+	if (!g_norm_bad_store[dev] && cudaMalloc(&g_norm_bad_store[dev], SSC_GENERIC_MAX_FRAMES * sizeof(unsigned int)) != cudaSuccess)
+		return SSC_ERR_CUDA;
+	k_verify_cheap_norm<<<n, 256, 0, stream>>>(p.coeff, n, p.normalize, g_norm_bad_store[dev]);
+	if (cudaGetLastError() != cudaSuccess) return SSC_ERR_CUDA;
+	p.norm_bad = g_norm_bad_store[dev];
+	return SSC_OK;
+}
+
 // frees the per-device scratch the kernels keep between launches (ssc_release_workspace)
 void release_kernel_scratch(int dev) {
 	if (dev < 0 || dev >= 64) return;
 	if (g_fit_store[dev]) { cudaFree(g_fit_store[dev]); g_fit_store[dev] = nullptr; }
+	if (g_norm_bad_store[dev]) { cudaFree(g_norm_bad_store[dev]); g_norm_bad_store[dev] = nullptr; }
 	LeftoverIdStore &ids = g_leftover_id_store[dev];
 	if (ids.ids) cudaFree(ids.ids);
 	if (ids.count) cudaFree(ids.count);
@@ -230,12 +274,17 @@ static int launch_stack_unchained(const StackParams &p_in, int is_median, cudaSt
 		int rc = fit_tables(p.fit, stream);
 		if (rc) return rc;
 	}
+	p.norm_bad = nullptr;
 	if (g_kernel_path != 1 && warp_path_eligible(p, is_median))
 		return launch_stack_warp(p, is_median, stream);
 	if (g_kernel_path != 1 && fast_path_eligible(p, is_median))
 		return launch_stack_fast(p, is_median, stream);
-	if (g_kernel_path != 1 && mid_path_eligible(p, is_median))
+	if (g_kernel_path != 1 && mid_path_eligible(p, is_median)) {
+		// this kernel normalizes with the cheap form where k_verify_cheap_norm allows it
+		int rc = verify_cheap_norm(p, stream);
+		if (rc) return rc;
 		return launch_stack_mid(p, is_median, stream);
+	}
 	return launch_stack_generic(p, nullptr, nullptr, 0, is_median, stream);
 }
 

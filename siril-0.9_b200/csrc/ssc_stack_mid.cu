@@ -40,9 +40,39 @@ __device__ __forceinline__ void bitonic_merge_64(unsigned int (&v)[64]) {
 	}
 }
 
-template <int KIND, int MID_THREADS, int NPAD>
+// s_coef: offset [f], mul [NPAD + f], scale [2 NPAD + f] -- or the constants of the cheap form (ssc_network.cuh):
+// multiplicative kinds a [2f], c [2f + 1]; additive kinds offset [f], c [NPAD + f], a [2 NPAD + f]
+template <int KIND, int MID_THREADS, int NPAD, bool CHEAP = false>
 __device__ __forceinline__ void normalize_column(unsigned int *col_t, const double *s_coef, int f_begin, int N,
 		unsigned int &Sa, unsigned int &Sb, unsigned long long &Qa, unsigned long long &Qb) {
+	if constexpr (CHEAP) {
+		constexpr bool MULT = KIND == MULTIPLICATIVE || KIND == MULTIPLICATIVE_SCALING;
+		unsigned int hi_a[4], hi_b[4];	// the high words of the 8 doubles in flight (cheap_sample)
+#pragma unroll
+		for (int j = 0; j < 4; j++) hi_a[j] = hi_b[j] = SSC_HI52;
+#pragma unroll 1
+		for (int f0 = f_begin; f0 < N; f0 += 4) {
+			unsigned int pa[4], pb[4];
+			double a[4], c[4], off[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const unsigned short *h = reinterpret_cast<const unsigned short *>(col_t + (f0 + j) * MID_THREADS);
+				pa[j] = lds_u16(h);
+				pb[j] = lds_u16(h + 1);
+				a[j] = MULT ? s_coef[2 * (f0 + j)] : s_coef[2 * NPAD + f0 + j];
+				c[j] = MULT ? s_coef[2 * (f0 + j) + 1] : s_coef[NPAD + f0 + j];
+				off[j] = MULT ? 0.0 : s_coef[f0 + j];
+			}
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				if (f0 + j >= N) break;
+				const unsigned int w = cheap_pair<KIND>(pa[j], pb[j], a[j], c[j], off[j], Qa, Qb, hi_a[j], hi_b[j]);
+				col_t[(f0 + j) * MID_THREADS] = w;
+				Sa = __dp2a_lo(w, 0x0001u, Sa);
+				Sb = __dp2a_lo(w, 0x0100u, Sb);
+			}
+		}
+	} else {
 #pragma unroll 1
 	for (int f0 = f_begin; f0 < N; f0 += 4) {	// frames [f_begin, N), f_begin a multiple of 4
 		unsigned int w[4];
@@ -70,6 +100,7 @@ __device__ __forceinline__ void normalize_column(unsigned int *col_t, const doub
 			Sb = __dp2a_lo(w[j], 0x0100u, Sb);
 		}
 	}
+	}
 }
 
 // NPAD: 128 .. 1024, the column length the merges work on (sentinels 0xFFFF behind the N samples);
@@ -79,7 +110,7 @@ __global__ void __launch_bounds__(2 * MID_THREADS)
 k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 	extern __shared__ unsigned int col[];			// [NPAD][MID_THREADS] packed columns
 	__shared__ double s_coef[3 * NPAD];			// offset, mul, scale
-	__shared__ int s_fast_norm;
+	__shared__ int s_fast_norm, s_cheap;
 	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
 	__shared__ unsigned long long s_S[4 * MID_THREADS], s_Q[4 * MID_THREADS];	// [half of the column][pixel * MID_THREADS + pair]
 	__shared__ unsigned int s_out[MID_THREADS];		// per pair: result index, bit 31 = inactive
@@ -91,18 +122,40 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 	const bool need_sort = is_median || p.rejection != NO_REJEC;
 
 	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
-	if (tid == 0) s_fast_norm = 1;
+	if (tid == 0) { s_fast_norm = 1; s_cheap = p.norm_bad != nullptr; }
 	__syncthreads();
+	for (int f = tid; f < N; f += 2 * MID_THREADS) {
+		if (!norm) break;
+		// domain of the 2^52 tricks (ssc_network.cuh): every intermediate stays below 2^31
+		if (!norm_domain_ok(p.normalize, p.coeff[f], p.coeff[N + f], p.coeff[2 * N + f])) s_fast_norm = 0;
+		if (p.norm_bad && p.norm_bad[f]) s_cheap = 0;	// the cheap form needs k_verify_cheap_norm's all-clear for every frame
+	}
+	__syncthreads();
+	const bool cheap = norm && s_fast_norm && s_cheap;
+	const bool cheap_mult = cheap && p.normalize != ADDITIVE && p.normalize != ADDITIVE_SCALING;
 	for (int f = tid; f < NPAD; f += 2 * MID_THREADS) {
 		const bool have = norm && f < N;
 		const double off = have ? p.coeff[f] : 0.0, mul = have ? p.coeff[N + f] : 1.0, sc = have ? p.coeff[2 * N + f] : 1.0;
-		s_coef[f] = off;
-		s_coef[NPAD + f] = mul;
-		s_coef[2 * NPAD + f] = sc;
-		if (have) {	// domain of the 2^52 tricks (ssc_network.cuh): every intermediate stays below 2^31
-			const bool additive = p.normalize == ADDITIVE || p.normalize == ADDITIVE_SCALING;
-			const double bound = additive ? dadd(dmul(fabs(sc), 65535.0), fabs(off)) : dmul(dmul(fabs(sc), 65535.0), fabs(mul));
-			if (!(bound < 2147483000.0)) s_fast_norm = 0;
+		if (!cheap) {
+			s_coef[f] = off;
+			s_coef[NPAD + f] = mul;
+			s_coef[2 * NPAD + f] = sc;
+		} else {	// the cheap form's constants (layout: normalize_column)
+			double a = 1.0, c = 0.0;
+			switch (p.normalize) {
+			case ADDITIVE: cheap_constants<ADDITIVE>(off, mul, sc, a, c); break;
+			case ADDITIVE_SCALING: cheap_constants<ADDITIVE_SCALING>(off, mul, sc, a, c); break;
+			case MULTIPLICATIVE: cheap_constants<MULTIPLICATIVE>(off, mul, sc, a, c); break;
+			default: cheap_constants<MULTIPLICATIVE_SCALING>(off, mul, sc, a, c); break;
+			}
+			if (cheap_mult) {
+				s_coef[2 * f] = a;
+				s_coef[2 * f + 1] = c;
+			} else {
+				s_coef[f] = off;
+				s_coef[NPAD + f] = c;
+				s_coef[2 * NPAD + f] = a;
+			}
 		}
 	}
 	__syncthreads();
@@ -156,6 +209,13 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median) {
 				Sa += pa; Sb += pb;
 				Qa += (unsigned long long) pa * pa;
 				Qb += (unsigned long long) pb * pb;
+			}
+		} else if (cheap) {
+			switch (p.normalize) {
+			case ADDITIVE: normalize_column<ADDITIVE, MID_THREADS, NPAD, true>(col_t, s_coef, h0, n_end, Sa, Sb, Qa, Qb); break;
+			case MULTIPLICATIVE: normalize_column<MULTIPLICATIVE, MID_THREADS, NPAD, true>(col_t, s_coef, h0, n_end, Sa, Sb, Qa, Qb); break;
+			case ADDITIVE_SCALING: normalize_column<ADDITIVE_SCALING, MID_THREADS, NPAD, true>(col_t, s_coef, h0, n_end, Sa, Sb, Qa, Qb); break;
+			default: normalize_column<MULTIPLICATIVE_SCALING, MID_THREADS, NPAD, true>(col_t, s_coef, h0, n_end, Sa, Sb, Qa, Qb); break;
 			}
 		} else {
 			switch (norm ? p.normalize : NO_NORM) {

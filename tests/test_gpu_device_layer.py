@@ -177,3 +177,48 @@ def test_non_finite_coefficients_are_deterministic(gpu):
                 finally:
                     gpu.set_kernel_path(0)
                 assert np.array_equal(out.cpu().numpy().view(np.uint16).ravel(), expect), (off, mul, sc, norm, path)
+
+
+@pytest.mark.parametrize("n,w", [(200, 32), (100, 48), (300, 16), (64, 64)])
+@pytest.mark.parametrize("norm", [1, 2, 3, 4])
+def test_one_fma_normalization_is_only_used_where_it_is_exact(gpu, port, n, w, norm):
+    """The 65..1024-frame kernel (ssc_stack_mid.cu) normalizes with one FMA per sample on launches whose coefficients
+    k_verify_cheap_norm cleared (all 65536 sample values of every frame equal to the reference's individually
+    rounded form, stacking.c:1635-1652 + round_to_WORD) and with the reference's form otherwise.  Coefficient sets
+    that hit exact .5 ties (where nearest-even and round-half-up part), negative, tiny and huge factors must
+    therefore give the oracle's image on every path -- and so must ordinary ones."""
+    import torch
+    dev = torch.device("cuda", 0)
+    sp = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(1000 * n + norm)
+    c, h = 1, 8
+    raw = rng.integers(0, 65536, size=(n, c, h, w), dtype=np.uint16)
+    raw[:, :, 0, :8] = np.array([0, 1, 2, 3, 65535, 65534, 32768, 32767], dtype=np.uint16)
+    fr = torch.tensor(raw.view(np.int16), device=dev)
+    sets = {
+        "ordinary": (rng.uniform(-300, 300, n), rng.uniform(0.8, 1.25, n), rng.uniform(0.8, 1.25, n)),
+        "ties": (rng.choice([0.5, -0.5, 1.5, 100.5, -0.25], n), rng.choice([0.5, 1.5, 0.75, 1.25, 1.0], n),
+                 rng.choice([0.5, 1.5, 2.5, 1.0, 0.25], n)),
+        "one bad frame": (np.r_[rng.uniform(-300, 300, n - 1), 0.5], np.r_[rng.uniform(0.8, 1.25, n - 1), 0.5],
+                          np.r_[rng.uniform(0.8, 1.25, n - 1), 1.5]),
+        "negative": (rng.uniform(-300, 300, n), -rng.uniform(0.8, 1.25, n), rng.uniform(0.8, 1.25, n)),
+        "tiny and huge": (rng.uniform(-3, 3, n), rng.choice([1e-9, 3e-5, 7.0, 900.0, 2e4], n), rng.choice([1e-7, 0.013, 33.0], n)),
+    }
+    for name, (off, mul, sc) in sets.items():
+        if norm in (1, 2):
+            sc = np.ones(n)            # compute_normalization leaves scale at 1.0 in these modes (stacking.c:130-134)
+        coeff_h = np.array([off, mul, sc], dtype=np.float64)
+        coeff = torch.tensor(coeff_h, device=dev)
+        want = port.stack_mean(raw, 2, (4.0, 3.0), norm, coeff=coeff_h, sd_mode=port.SD_EXACT)
+        for path in (0, 2, 1):
+            gpu.set_kernel_path(path)
+            try:
+                out = torch.zeros((c, h, w), dtype=torch.int16, device=dev)
+                cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+                gpu.dev.stack_mean(gpu.dev.band(fr.data_ptr(), n, c, h, w), out.data_ptr(), cnt.data_ptr(), 2,
+                                   (4.0, 3.0), norm, coeff.data_ptr(), stream=sp)
+                torch.cuda.synchronize()
+            finally:
+                gpu.set_kernel_path(0)
+            assert np.array_equal(out.cpu().numpy().view(np.uint16), want["out"]), (name, norm, path)
+            assert np.array_equal(cnt.cpu().numpy()[:6].reshape(3, 2), want["irej"]), (name, norm, path)

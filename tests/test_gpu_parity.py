@@ -291,7 +291,7 @@ def test_register_network_kernel_equals_general_kernel(gpu, port, rej, n, norm):
     columns) must be interchangeable: same image, counters and guard events, both equal to the oracle."""
     fr = synth.make_frames(n, 1, 24, 64, seed=n + norm, outlier_p=8e-3, zero_p=2e-3, stars=3)
     outs = []
-    for path in (0, 1):                                      # automatic, general kernel
+    for path in (0, 1, 2):                                   # automatic, general kernel, automatic with the exact normalization
         gpu.set_kernel_path(path)
         try:
             if rej == "median":
@@ -324,7 +324,7 @@ def test_mid_kernel_equals_general_kernel(gpu, port, rej, n, norm):
     h, w = (12, 48) if n <= 256 else (6, 40)
     fr = synth.make_frames(n, 1, h, w, seed=n + norm, outlier_p=8e-3, zero_p=2e-3, stars=2)
     outs = []
-    for path in (0, 1):                                      # automatic (mid kernel), general kernel
+    for path in (0, 1, 2):                                   # automatic (mid kernel), general kernel, exact normalization
         gpu.set_kernel_path(path)
         try:
             if rej == "median":
@@ -335,9 +335,10 @@ def test_mid_kernel_equals_general_kernel(gpu, port, rej, n, norm):
         finally:
             gpu.set_kernel_path(0)
         outs.append(res)
-    a, b = outs
-    assert np.array_equal(a.data, b.data)
-    assert np.array_equal(a.irej, b.irej) and a.guard_fired == b.guard_fired and a.cap_hit == b.cap_hit
+    a = outs[0]
+    for b in outs[1:]:
+        assert np.array_equal(a.data, b.data)
+        assert np.array_equal(a.irej, b.irej) and a.guard_fired == b.guard_fired and a.cap_hit == b.cap_hit
     if rej == "median":
         assert np.array_equal(a.data, port.stack_median(fr, normalize=norm, coeff=a.coeff)["out"])
     else:
