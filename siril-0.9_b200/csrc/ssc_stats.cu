@@ -326,16 +326,26 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 		}
 		__syncthreads();
 		uint32_t run = wsum[warp];
-		for (int k = 0; k < 64; k++) {
-			const int bin = warp * 2048 + k * 32 + lane;
-			const uint32_t c = bin == 0 ? 0u : h[bin];
-			uint32_t incl = c;
-			for (int o = 1; o < 32; o <<= 1) {
-				uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-				if (lane >= o) incl += u;
+		for (int k = 0; k < 64; k += 4) {	// four independent warp scans at a time (the chain of shuffles was 64 scans long)
+			uint32_t incl[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const int bin = warp * 2048 + (k + j) * 32 + lane;
+				incl[j] = bin == 0 ? 0u : h[bin];
 			}
-			cum[bin] = run + incl;
-			run += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const uint32_t u = __shfl_up_sync(0xffffffffu, incl[j], o);
+					if (lane >= o) incl[j] += u;
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				cum[warp * 2048 + (k + j) * 32 + lane] = run + incl[j];
+				run += __shfl_sync(0xffffffffu, incl[j], 31);
+			}
 		}
 	}
 	__syncthreads();
@@ -351,6 +361,7 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 	}
 	__syncthreads();
 	const double norm = s_norm;
+	const Reciprocal inv_norm(norm);	// x / norm below: the same correctly rounded quotients from one real division (ssc_device.cuh)
 	const unsigned long long n_total = cum[65535];
 
 	for (int it = 0; it < SSC_ITER_CAP; it++) {
@@ -383,12 +394,12 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 				// median: bins holding ranks (n-1)/2 and n/2 (gsl_stats_median_from_sorted_data)
 				const unsigned long long rk[2] = {(n - 1) >> 1, n >> 1};
 				int kb[2];
-				for (int q = 0; q < 2; q++) {
-					const unsigned long long rank = rk[q];
-					kb[q] = search(bi, bj - 1, [&](int k) { return (unsigned long long) cum[k] - base > rank; });
-				}
-				double dl = ddiv((double) kb[0], norm), dr = ddiv((double) kb[1], norm);
-				double m = rk[0] == rk[1] ? dl : ddiv(dadd(dl, dr), 2.0);
+				kb[0] = search(bi, bj - 1, [&](int k) { return (unsigned long long) cum[k] - base > rk[0]; });
+				// (rank n/2 sits in the same bin as rank (n-1)/2 unless that bin ends exactly there: one probe, then the search)
+				kb[1] = (unsigned long long) cum[kb[0]] - base > rk[1] ? kb[0]
+						: search(kb[0] + 1, bj - 1, [&](int k) { return (unsigned long long) cum[k] - base > rk[1]; });
+				double dl = inv_norm.divide((double) kb[0]), dr = inv_norm.divide((double) kb[1]);
+				double m = rk[0] == rk[1] ? dl : dmul(dadd(dl, dr), 0.5);	// (x / 2.0 == x * 0.5 exactly)
 				// MAD (statistics.c:83-100): order statistics of |d_k - m|.  With M2 = kb0 + kb1
 				// (twice the median in bin units) bins order by the integer distance
 				// u_k = |2k - M2|; only the mirror pair (k, M2 - k) ties, and there the FP
@@ -402,16 +413,22 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 					return khi >= klo ? (unsigned long long) cum[khi] - cum[klo - 1] : 0ull;
 				};
 				double dv[2];
+				// the largest distance any bin of the window has: count_within(u_max) = n > rank
+				const int u_max = max(M2 - 2 * bi, 2 * (bj - 1) - M2);
+				int u_prev = 0;
 				for (int q = 0; q < 2; q++) {
 					const unsigned long long rank = rk[q];
-					const int u = search(0, 2 * 65536, [&](int uu) { return count_within(uu) > rank; });
+					// (the second rank: the same distance unless the count ends exactly there -- one probe, then the search)
+					const int u = q == 1 && count_within(u_prev) > rank ? u_prev
+							: search(q == 1 ? u_prev + 1 : 0, u_max, [&](int uu) { return count_within(uu) > rank; });
+					u_prev = u;
 					const unsigned long long below = u > 0 ? count_within(u - 1) : 0ull;	// C(u - 1)
 					const int k1 = (M2 - u) >> 1, k2 = (M2 + u) >> 1;	// exact: u has M2's parity here
 					const bool in1 = (M2 - u) >= 0 && k1 >= bi && k1 < bj;
 					const bool in2 = k2 != k1 && k2 >= bi && k2 < bj;
 					const unsigned long long c1 = in1 ? (unsigned long long) cum[k1] - cum[k1 - 1] : 0ull;
-					const double d1 = fabs(dsub(ddiv((double) k1, norm), m));
-					const double d2 = fabs(dsub(ddiv((double) k2, norm), m));
+					const double d1 = fabs(dsub(inv_norm.divide((double) k1), m));
+					const double d2 = fabs(dsub(inv_norm.divide((double) k2), m));
 					const unsigned long long pos = rk[q] - below;
 					if (!in2) dv[q] = d1;
 					else if (!in1) dv[q] = d2;
@@ -424,7 +441,7 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 				if (lane == 0) {
 					s_n = n;
 					s_m = m;
-					s_mad = rk[0] == rk[1] ? dv[0] : ddiv(dadd(dv[0], dv[1]), 2.0);
+					s_mad = rk[0] == rk[1] ? dv[0] : dmul(dadd(dv[0], dv[1]), 0.5);
 				}
 			}
 		}
@@ -436,7 +453,7 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 		const int bi = s_bi, bj = s_bj;
 		double u = 0.0, w = 0.0;
 		if (mad > 0.0) {
-			const Reciprocal inv_mad9(dmul(9.0, mad)), inv_norm(norm);
+			const Reciprocal inv_mad9(dmul(9.0, mad));
 			// thread t takes bins bi + t, bi + t + 1024, ... of the clipping window: the window (a few
 			// hundred bins after the first iteration) is spread over all threads, loads coalesce
 			for (int bin = bi + tid; bin < bj; bin += IKSS_THREADS) {
@@ -482,14 +499,14 @@ k_ikss(const uint32_t *__restrict__ hist, double *__restrict__ stats, uint32_t *
 					double g = dmul(xlow, norm);
 					int k = g > 3.0 ? (int) g - 2 : 0;
 					if (k < bi) k = bi;
-					while (k < bj && ddiv((double) k, norm) < xlow) k++;
+					while (k < bj && inv_norm.divide((double) k) < xlow) k++;
 					nbi = k;
 				}
 				{	// last bin < bj with d_k <= xhigh
 					double g = dmul(xhigh, norm);
 					int k = g < 65533.0 ? (int) g + 2 : 65535;
 					if (k > bj - 1) k = bj - 1;
-					while (k >= nbi && ddiv((double) k, norm) > xhigh) k--;
+					while (k >= nbi && inv_norm.divide((double) k) > xhigh) k--;
 					nbj = k + 1;
 				}
 				s_bi = nbi;
