@@ -104,6 +104,46 @@ __device__ __forceinline__ int sigma_pass_sorted(Column c, int &o, int &N, doubl
 	return n;
 }
 
+// The straight line of LINEARFIT (stacking.c:1750-1768) through the N sorted samples c[0 .. N): gsl_fit_linear with
+// x_i = i (GSL fit/linear.c) as its literal running means -- 4 N individually rounded updates -- then the mean absolute
+// residual in the reference's summation order.  a = slope, b = intercept.  With the tables (FitTables) the
+// data-independent recurrences (mean of x, mean of dx^2) are looked up and every division by i + 1 becomes
+// div_exact() with RN(1 / (i + 1)): same bits, ~5x less work.
+static __device__ __forceinline__ void fit_line_literal(Column c, int N, const FitTables *fit, double &a, double &b, double &sigma) {
+	double m_x = 0.0, m_y = 0.0, m_dx2 = 0.0, m_dxdy = 0.0;
+	const bool tab = fit && N <= fit->n_max;
+	if (tab) {
+		m_x = fit->mx[N];
+		m_dx2 = fit->mdx2[N];
+		for (int i = 0; i < N; i++)
+			m_y = dadd(m_y, div_exact(dsub((double) (int) c.get(i), m_y), (double) (i + 1), fit->inv[i + 1]));
+		for (int i = 0; i < N; i++) {
+			double dx = dsub((double) i, m_x);
+			double dy = dsub((double) (int) c.get(i), m_y);
+			m_dxdy = dadd(m_dxdy, div_exact(dsub(dmul(dx, dy), m_dxdy), (double) (i + 1), fit->inv[i + 1]));
+		}
+	} else {
+		for (int i = 0; i < N; i++) {
+			double ip1 = dadd((double) i, 1.0);
+			m_x = dadd(m_x, ddiv(dsub((double) i, m_x), ip1));
+			m_y = dadd(m_y, ddiv(dsub((double) (int) c.get(i), m_y), ip1));
+		}
+		for (int i = 0; i < N; i++) {
+			double ip1 = dadd((double) i, 1.0);
+			double dx = dsub((double) i, m_x);
+			double dy = dsub((double) (int) c.get(i), m_y);
+			m_dx2 = dadd(m_dx2, ddiv(dsub(dmul(dx, dx), m_dx2), ip1));
+			m_dxdy = dadd(m_dxdy, ddiv(dsub(dmul(dx, dy), m_dxdy), ip1));
+		}
+	}
+	a = ddiv(m_dxdy, m_dx2);		// slope
+	b = dsub(m_y, dmul(m_x, a));		// intercept
+	sigma = 0.0;
+	for (int f = 0; f < N; f++)
+		sigma = dadd(sigma, fabs(dsub((double) (int) c.get(f), dadd(dmul(a, (double) f), b))));
+	sigma = ddiv(sigma, (double) N);
+}
+
 // stacking.c:1656-1794 for one column whose N samples are sorted ascending in
 // c[0..N) with S = sum, Q = sum of squares.  Returns the output sample.
 // tables: optional small-n tables (ssc_device.cuh) that replace the divisions, bit for bit.
@@ -228,41 +268,8 @@ static __device__ __noinline__ unsigned int reject_sorted_and_mean(Column c, int
 		break;
 	case LINEARFIT:		// stacking.c:1750-1784
 		do {
-			// gsl_fit_linear with x_i = i (GSL fit/linear.c), literal running means.  With the tables
-			// (FitTables) the data-independent recurrences (mean of x, mean of dx^2) are looked up and
-			// every division by i + 1 becomes div_exact() with RN(1 / (i + 1)): same bits, ~5x less work.
-			double m_x = 0.0, m_y = 0.0, m_dx2 = 0.0, m_dxdy = 0.0;
-			const bool tab = fit && N <= fit->n_max;
-			if (tab) {
-				m_x = fit->mx[N];
-				m_dx2 = fit->mdx2[N];
-				for (int i = 0; i < N; i++)
-					m_y = dadd(m_y, div_exact(dsub((double) (int) c.get(i), m_y), (double) (i + 1), fit->inv[i + 1]));
-				for (int i = 0; i < N; i++) {
-					double dx = dsub((double) i, m_x);
-					double dy = dsub((double) (int) c.get(i), m_y);
-					m_dxdy = dadd(m_dxdy, div_exact(dsub(dmul(dx, dy), m_dxdy), (double) (i + 1), fit->inv[i + 1]));
-				}
-			} else {
-				for (int i = 0; i < N; i++) {
-					double ip1 = dadd((double) i, 1.0);
-					m_x = dadd(m_x, ddiv(dsub((double) i, m_x), ip1));
-					m_y = dadd(m_y, ddiv(dsub((double) (int) c.get(i), m_y), ip1));
-				}
-				for (int i = 0; i < N; i++) {
-					double ip1 = dadd((double) i, 1.0);
-					double dx = dsub((double) i, m_x);
-					double dy = dsub((double) (int) c.get(i), m_y);
-					m_dx2 = dadd(m_dx2, ddiv(dsub(dmul(dx, dx), m_dx2), ip1));
-					m_dxdy = dadd(m_dxdy, ddiv(dsub(dmul(dx, dy), m_dxdy), ip1));
-				}
-			}
-			const double a = ddiv(m_dxdy, m_dx2);		// slope
-			const double b = dsub(m_y, dmul(m_x, a));	// intercept
-			sigma = 0.0;
-			for (int f = 0; f < N; f++)
-				sigma = dadd(sigma, fabs(dsub((double) (int) c.get(f), dadd(dmul(a, (double) f), b))));
-			sigma = ddiv(sigma, (double) N);
+			double a, b;
+			fit_line_literal(c, N, fit, a, b, sigma);	// gsl_fit_linear's literal running means, mean absolute residual
 			const Reciprocal inv_sigma(sigma);	// line_clipping divides every residual by sigma (:1175,1179)
 			int out = 0, f = 0;
 			for (; f < N; f++) {

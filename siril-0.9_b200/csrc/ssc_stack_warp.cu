@@ -20,9 +20,9 @@
 //      outside the margin -- which covers the rounding of both formulations by three orders of
 //      magnitude -- the flags are the ones the reference's arithmetic produces, and the result is
 //      bit-identical to it (oracle/siril_oracle.c restates both forms; tests/test_oracle_kat.py).
-//      A pixel with a comparison inside the margin (an exact tie, a vanishing sigma) is handed back by
-//      index and finished by the general kernel with gsl_fit_linear's literal recurrences
-//      (ssc_column.cuh), so no result ever depends on the screening arithmetic;
+//      A PASS with a comparison inside the margin (an exact tie, a vanishing sigma) takes its line and sigma from
+//      gsl_fit_linear's literal recurrences instead (ssc_column.cuh:fit_line_literal, one lane, out of line), and its
+//      flags from line_clipping itself, so no result ever depends on the screening arithmetic;
 //   4. the reference's `if (N - r <= 4) break;` (stacking.c:1771) is applied from prefix counts of the
 //      flags: the samples behind the break keep flag 0, the event is counted (guard_fired).
 #include <algorithm>
@@ -118,13 +118,45 @@ __device__ __forceinline__ int warp_scan(int x, const int lane) {
 	return x;
 }
 
+// One clipping pass with the reference's own arithmetic -- the rare pass the screening below cannot decide (a comparison
+// inside the margin, a vanishing sigma).  The survivors are compacted in order, ONE lane runs gsl_fit_linear's literal
+// recurrences and the residual sum in the reference's order (ssc_column.cuh:fit_line_literal: 3 n strictly sequential
+// rounded updates), then every lane flags its own samples with line_clipping (stacking.c:1170-1183) at their ranks.
+// Out of line and rolled, reading the samples from the warp's shared-memory copy: the screening is straight-line code
+// on registers and must not notice this path.  y: this lane's samples (y[r * 32]), alive: which of them survive,
+// base: rank of the first of them among the survivors.
+static __device__ __noinline__ void literal_pass(const double *y, unsigned int alive, int base, int n_cur, int lane, int rows,
+		double slow, double shigh, FitTables fit, WORD *comp, unsigned int *masks) {
+	int k = base;
+	for (int r = 0; r < rows; r++)
+		if (alive & (1u << r)) comp[k++] = (WORD) __double2int_rn(y[r * 32]);
+	__syncwarp();
+	double a = 0.0, b = 0.0, sigma = 0.0;
+	if (lane == 0) fit_line_literal(Column{comp, 1}, n_cur, &fit, a, b, sigma);
+	a = __shfl_sync(FULL, a, 0); b = __shfl_sync(FULL, b, 0); sigma = __shfl_sync(FULL, sigma, 0);
+	const Reciprocal inv_sigma(sigma);	// line_clipping divides every residual by sigma (:1175,1179)
+	unsigned int fm = 0, lom = 0;
+	k = base;
+	for (int r = 0; r < rows; r++) {
+		if (alive & (1u << r)) {
+			const int fl = clip_line(inv_sigma, (unsigned int) __double2int_rn(y[r * 32]), slow, shigh, k, a, b);
+			if (fl) fm |= 1u << r;
+			if (fl < 0) lom |= 1u << r;
+			k++;
+		}
+	}
+	__syncwarp();
+	masks[0] = fm; masks[1] = lom;
+}
+
 // ---------------------------------------------------------------------------------------------
-// linear-fit clipping of one pixel (half `sel` of the packed column).  false: hand the pixel back.
+// linear-fit clipping of one pixel (half `sel` of the packed column).  Always finishes the pixel (true); the
+// hand-back list of the earlier form stays for the operator layer's protocol but is no longer fed from here.
 // ---------------------------------------------------------------------------------------------
 template <int R>
 __device__ __forceinline__ bool fit_pixel(const unsigned int (&v)[R], const int sel, const int N, const int lane,
-		const double slow, const double shigh, const FitTables &fit, double *__restrict__ y, unsigned int &result,
-		unsigned int &rej_lo, unsigned int &rej_hi, int &guard, int &cap) {
+		const double slow, const double shigh, const FitTables &fit, double *__restrict__ y, WORD *__restrict__ comp,
+		unsigned int &result, unsigned int &rej_lo, unsigned int &rej_hi, int &guard, int &cap) {
 	// y: this lane's R samples as doubles, in the warp's own piece of shared memory (y[r * 32]: conflict-free;
 	// in registers they would cost 2 R of them next to the packed column)
 	unsigned int alive = 0, Sy = 0, Wl = 0;	// Sy = sum of my live samples, Wl = sum of (rank inside the lane) * sample
@@ -161,7 +193,7 @@ __device__ __forceinline__ bool fit_pixel(const unsigned int (&v)[R], const int 
 			add_if(pred, a, on);
 		}
 		const double sigma = dmul(warp_sum(t), fit.inv[n_cur]);
-		if (!(sigma > 0.05)) return false;	// (nearly) perfect line: the reference divides by this sigma
+		bool literal = !(sigma > 0.05);	// (nearly) perfect line: the reference divides by this sigma
 		const double tl = dmul(slow, sigma), th = dmul(shigh, sigma);
 		const double ml = dadd(dmul(fabs(tl), 1e-7), 1e-6), mh = dadd(dmul(fabs(th), 1e-7), 1e-6);
 		const double tl_s = dadd(tl, ml), tl_m = dsub(tl, ml), th_s = dadd(th, mh), th_m = dsub(th, mh);
@@ -177,7 +209,15 @@ __device__ __forceinline__ bool fit_pixel(const unsigned int (&v)[R], const int 
 			lom |= lo_s ? on : 0u;				// line_clipping tests the low side first (:1175)
 			fm |= (lo_s | hi_s) ? on : 0u;
 		}
-		if (__any_sync(FULL, near != 0)) return false;
+		literal = literal || __any_sync(FULL, near != 0);
+		if (literal) {
+			// ITS flags come from the reference's own arithmetic; the passes before and after keep the screening form, and
+			// every flag is the reference's either way.  (The first form handed the whole pixel to a second kernel that
+			// redid all its passes literally: a 5 ms chain per launch for a few hundred pixels.)
+			unsigned int masks[2];
+			literal_pass(y, alive, base, n_cur, lane, R, slow, shigh, fit, comp, masks);
+			fm = masks[0]; lom = masks[1];
+		}
 		// the reference's scan: r++ per flagged sample, `if (N - r <= 4) break;` after every sample
 		const int c = __popc(fm);
 		const int e = warp_scan(c, lane) - c;
@@ -244,6 +284,7 @@ k_stack_warp(StackParams p, unsigned int n_pairs, int is_median, LeftoverList li
 	const int W = b.width, W2 = W >> 1, N = b.n_frames, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
 	double *s_y = s_fit + (size_t) warp * 32 * R + lane;
+	WORD *s_comp = reinterpret_cast<WORD *>(s_fit + (size_t) WARP_PAIRS * 32 * R) + (size_t) warp * 32 * R;	// survivors in order (literal passes)
 	const unsigned long long fstride = (unsigned long long) b.frame_stride * sizeof(WORD);
 	const unsigned int warps_total = gridDim.x * WARP_PAIRS;
 	unsigned long long cnt[SSC_COUNTERS] = {0, 0, 0, 0, 0, 0, 0, 0};	// lane 0: this warp's share of the counters
@@ -309,7 +350,7 @@ k_stack_warp(StackParams p, unsigned int n_pairs, int is_median, LeftoverList li
 		for (int sel = 0; sel < 2; sel++) {
 			unsigned int res = 0, rej_lo = 0, rej_hi = 0;
 			int guard = 0, cap = 0;
-			const bool done = fit_pixel<R>(v, sel, N, lane, p.sig_low, p.sig_high, p.fit, s_y, res, rej_lo, rej_hi, guard, cap);
+			const bool done = fit_pixel<R>(v, sel, N, lane, p.sig_low, p.sig_high, p.fit, s_y, s_comp, res, rej_lo, rej_hi, guard, cap);
 			__syncwarp();
 			if (lane == 0) {
 				if (done) {
@@ -434,7 +475,7 @@ static int launch_warp(const StackParams &p, int is_median, cudaStream_t stream)
 	if (pairs == 0) return SSC_OK;
 	if (pairs >= 0xFFFFFFF0ull) return SSC_ERR_ARG;
 	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
-	const size_t smem = (is_median && !norm) ? 0 : (size_t) WARP_PAIRS * 32 * R * sizeof(double);	// the fit's doubles / the normalization's copy
+	const size_t smem = (is_median && !norm) ? 0 : (size_t) WARP_PAIRS * 32 * R * (sizeof(double) + (is_median ? 0 : sizeof(WORD)));	// the fit's doubles (+ the compacted survivors of a literal pass) / the normalization's copy
 	if (cudaFuncSetAttribute(k_stack_warp<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess)
 		return SSC_ERR_CUDA;
 	LeftoverList list{nullptr, 0, nullptr, nullptr};
