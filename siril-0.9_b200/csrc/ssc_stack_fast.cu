@@ -683,6 +683,9 @@ k_sigma_handback(StackParams p, LeftoverList list) {
 	__shared__ double s_unbias[65], s_inv_n[65], s_inv_n2[65];
 	__shared__ unsigned long long blk_counters[SSC_COUNTERS];
 	const int tid = threadIdx.x;
+	unsigned int n_items = *list.count;
+	if (n_items > list.capacity) n_items = list.capacity;
+	if (blockIdx.x * 128u >= n_items) return;	// (usually the whole grid: the launch then costs its latency only)
 	if (tid < SSC_COUNTERS) blk_counters[tid] = 0;
 	if (tid >= 1 && tid <= 64) {
 		s_unbias[tid] = tid > 1 ? ddiv((double) tid, (double) (tid - 1)) : 0.0;
@@ -694,8 +697,6 @@ k_sigma_handback(StackParams p, LeftoverList list) {
 	const ssc_band &b = p.band;
 	const int W = b.width;
 	const bool norm = p.coeff != nullptr && p.normalize != NO_NORM;
-	unsigned int n_items = *list.count;
-	if (n_items > list.capacity) n_items = list.capacity;
 	for (unsigned int base = blockIdx.x * 128; base < n_items; base += gridDim.x * 128) {
 		const unsigned int i = base + tid;
 		if (i < n_items) {

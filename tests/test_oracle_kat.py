@@ -128,3 +128,50 @@ def test_fit_formulations_agree(port):
     a = port.reject_column(tie, port.LINEARFIT, (5.0, 2.5), port.SD_EXACT)
     b = port.reject_column(tie, port.LINEARFIT, (5.0, 2.5), port.SD_EXACT | port.FIT_EXACT)
     assert a[0] != b[0]                                      # rounding noise decides an exact tie
+
+
+# --------------------------------------------------------------------------- the one-FMA normalization
+def _cheap_form(p, mode, off, mul, sc):
+    """csrc/ssc_network.cuh:cheap_sample restated with exact rationals (an FMA rounds once: float(Fraction) is the
+    correctly rounded quotient of two integers).  Returns the WORD the kernel would produce."""
+    from fractions import Fraction as F
+    two52, magic = 4503599627370496.0, 6755399441055744.0
+    d = F(two52) + p                                                    # the register pair {p, 0x43300000}
+    if mode in (2, 4):                                                  # multiplicative kinds
+        a = float(np.float64(sc) * np.float64(mul)) if mode == 4 else mul
+        c = float(F(-two52) * F(a) + F(two52))                          # fma(-2^52, a, 2^52)
+        u = float(d * F(a) + F(c))                                      # fma(2^52 + p, a, c) = 2^52 + RN_int(p a)
+        v = int(u - two52)
+    else:                                                               # additive kinds
+        a = sc if mode == 3 else 1.0
+        c = float(np.float64(-two52) * np.float64(a))
+        t = float(d * F(a) + F(c))                                      # = RN(p a)
+        u = float(np.float64(t) - np.float64(off)) + magic              # (t - off) + 1.5 2^52, each rounded
+        v = int(u - magic)
+    return min(max(v, 0), 65535)
+
+
+def _reference_form(p, mode, off, mul, sc):
+    x = np.float64(p)
+    y = x * np.float64(sc) - np.float64(off) if mode in (1, 3) else (x * np.float64(sc)) * np.float64(mul)   # stacking.c:1640-1650
+    if not y > 0:
+        return 0
+    return 65535 if y > 65535.0 else int(y + np.float64(0.5))           # round_to_WORD, utils.c:68-74
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+def test_one_fma_normalization_model(mode):
+    """The kernels' one-FMA form of the normalization equals the reference's individually rounded form for ordinary
+    coefficients and differs from it at exact .5 ties (nearest-even against round-half-up) -- which is why the library
+    only uses it on launches where k_verify_cheap_norm found all 65536 sample values of every frame equal
+    (tests/test_gpu_device_layer.py runs that on the device)."""
+    rng = np.random.default_rng(mode)
+    samples = np.r_[0:300, 32760:32776, 65000:65536, rng.integers(0, 65536, 1500)]
+    for _ in range(3):                                                  # ratios of IKSS estimates: no ties in reach
+        off, mul, sc = rng.uniform(-300, 300), rng.uniform(0.8, 1.25), rng.uniform(0.8, 1.25)
+        if mode in (1, 2):
+            sc = 1.0                                                    # stacking.c:130-134
+        assert all(_cheap_form(int(p), mode, off, mul, sc) == _reference_form(int(p), mode, off, mul, sc) for p in samples)
+    off, mul, sc = 0.5, 0.5, (1.0 if mode in (1, 2) else 0.5)           # half-integer products on every other sample
+    differ = [int(p) for p in range(1, 64) if _cheap_form(p, mode, off, mul, sc) != _reference_form(p, mode, off, mul, sc)]
+    assert differ, "ties must separate the two forms (otherwise the verification would be pointless)"
