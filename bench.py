@@ -44,8 +44,8 @@ DRAM_BYTES_N1 = {
     "cfg1": (33_564_928, "profiles/r02_ncu_cfg1_sum.txt (k_sum_rows_vec8, whole image)"),
     "cfg2": (1_074_024_000 + 34_832_896, "profiles/r02_ncu_cfg2_median.txt (whole image)"),
     "cfg3": (9_252_995_000 + 163_980_288, "profiles/r01_ncu_k_stack_fast_full_size_launch.txt (whole image)"),
-    "cfg4": (8 * (821_562_880 + 37_642_752), "profiles/r02_ncu_cfg4_mid.txt (440-row slice = 1/8 of the image, x 8)"),
-    "cfg5": (8 * (692_242_432 + 12_340_992), "profiles/r02_ncu_cfg5_warp_final.txt (152-row slice = 1/8 of the image, x 8)"),
+    "cfg4": (8 * (822_657_792 + 65_631_488), "profiles/r02_ncu_cfg4_mid_v2.txt (440-row slice = 1/8 of the image, x 8)"),
+    "cfg5": (8 * (964_913_408 + 232_188_160), "profiles/r02_ncu_cfg5_warp_literal_pass.txt (152-row slice = 1/8 of the image, x 8; includes the kernel's local-memory traffic)"),
 }
 DOMINANT = {
     "cfg1": "k_sum_rows_vec8 (K1: per-pixel u32 sums + max)",
