@@ -158,6 +158,89 @@ def test_mid_kernel_merge_schedule_sorts(n, npad):
         assert (out[n:] == 0xFFFF).all()
 
 
+def mid_kernel_schedule_virtual(col, n, npad, net64):
+    """The same schedule as ssc_stack_mid.cu runs it since the virtual sentinels: only n_alloc = n rounded up to 8 rows are
+    STORED (an index at or beyond n_alloc raises here), every loop is bounded as in the kernel -- a compare-exchange whose
+    upper element would be a sentinel at or beyond n_alloc is skipped -- and one loop over the levels L = 32 (the runs of
+    64 through the network), 64 .. HALF/2 (merges inside a half), HALF (the shared last level) drives one register step."""
+    n_alloc = min(npad, (n + 7) & ~7)
+    v = np.full(n_alloc, 0xFFFF, dtype=np.int64)        # rows n .. n_alloc-1: stored sentinels
+    v[:n] = col
+    half = npad // 2
+
+    def ce(a, b):
+        assert a < b < n_alloc
+        v[a], v[b] = min(v[a], v[b]), max(v[a], v[b])
+
+    def register_step(c0, sort):                        # load_64 / sort_network or bitonic_merge_64 / store_64
+        blk = np.array([v[c0 + k] if c0 + k < n_alloc else 0xFFFF for k in range(64)], dtype=np.int64)
+        if sort:
+            for a, b in net64:
+                blk[a], blk[b] = min(blk[a], blk[b]), max(blk[a], blk[b])
+        else:
+            d = 32
+            while d >= 1:
+                for i in range(64):
+                    if (i & d) == 0:
+                        blk[i], blk[i + d] = min(blk[i], blk[i + d]), max(blk[i], blk[i + d])
+                d >>= 1
+        for k in range(64):
+            if c0 + k < n_alloc:
+                v[c0 + k] = blk[k]
+            else:
+                assert blk[k] == 0xFFFF                 # what is not stored must still be a sentinel
+
+    def half_cleaners(first, length, d_first):
+        d = d_first
+        while d >= 64:
+            for sb in range(first, first + length, 2 * d):
+                for i in range(sb, min(sb + d, n_alloc - d)):
+                    ce(i, i + d)
+            d >>= 1
+
+    L = 32
+    while L <= half:                                    # (the two threads of a pair run this loop side by side)
+        for hf in (0, 1):
+            h0 = hf * half
+            n_end = min(max(n, h0), h0 + half)
+            if 64 <= L < half:
+                for base in range(h0, h0 + half, 2 * L):
+                    for k in range(max(0, base + 2 * L - n_alloc), L):
+                        ce(base + k, base + 2 * L - 1 - k)
+            elif L == half:
+                for j in range(max(hf * (half // 2), npad - n_alloc), (hf + 1) * (half // 2)):
+                    ce(j, npad - 1 - j)
+        for hf in (0, 1):                               # (after the barrier that follows the shared stage)
+            h0 = hf * half
+            n_end = min(max(n, h0), h0 + half)
+            if L >= 64:
+                half_cleaners(h0, half, L >> 1)
+            c_end = n_end if L == 32 else min(h0 + half, n_alloc)
+            for c0 in range(h0, c_end, 64):
+                register_step(c0, L == 32)
+        L <<= 1
+    return v, n_alloc
+
+
+@pytest.mark.parametrize("n,npad", [(65, 128), (72, 128), (100, 128), (127, 128), (128, 128), (129, 256), (136, 256), (193, 256),
+                                    (200, 256), (255, 256), (256, 256), (257, 512), (300, 512), (449, 512), (512, 512),
+                                    (513, 1024), (700, 1024), (1000, 1024), (1024, 1024)])
+def test_mid_kernel_schedule_with_virtual_sentinels_sorts(n, npad):
+    net64 = networks()[64]
+    rng = np.random.default_rng(1000 + n)
+    for trial in range(4):
+        hi = (4, 65536, 65536, 2)[trial]
+        col = rng.integers(0, hi, size=n)
+        if trial == 2:
+            col[rng.integers(0, n, size=n // 3)] = 65535        # real samples equal to the sentinel value
+        if trial == 3:
+            col = col * 65535
+        out, n_alloc = mid_kernel_schedule_virtual(col, n, npad, net64)
+        assert np.array_equal(out[:n], np.sort(col))
+        assert (out[n:n_alloc] == 0xFFFF).all()
+        assert np.array_equal(out[:n], mid_kernel_schedule(col, n, npad, net64)[:n])
+
+
 def test_single_precision_no_rejection_proof_is_conservative():
     """ssc_stack_fast.cu:clip_cannot_fire decides "the first sigma-clipping pass rejects nothing" in FP32;
     it must never say so when the exact FP64 test (M2 - 2 min > floor(2 sig_low sigma), likewise above)
