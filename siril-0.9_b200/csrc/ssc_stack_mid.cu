@@ -252,7 +252,6 @@ k_stack_mid(StackParams p, unsigned int n_tiles, int is_median, int n_alloc) {
 		}
 		}
 
-		// the last six stages of a bitonic merge for the 64-element blocks of [first, first + len)
 		// 64 rows of the column into registers and back; rows at or beyond n_alloc are the virtual sentinels
 		auto load_64 = [&](unsigned int (&v)[64], int c0) {
 			const unsigned int *blk = col_t + c0 * MID_THREADS;
