@@ -62,7 +62,9 @@ __device__ __forceinline__ void lane_sort(unsigned int (&v)[R]) {
 template <int R>
 __device__ __forceinline__ void warp_sort(unsigned int (&v)[R], const int lane) {
 	lane_sort<R>(v);
-#pragma unroll
+	// (the five levels are ONE rolled loop: unrolled they were 3 k of the kernel's 14 k instructions, streamed through the
+	// instruction cache once per pixel pair)
+#pragma unroll 1
 	for (int m = 1; m <= 16; m <<= 1) {	// runs of m lanes -> runs of 2 m lanes
 		{	// element k of the lower run against element 2 m R - 1 - k of the upper run
 			unsigned int q[R];
@@ -72,7 +74,7 @@ __device__ __forceinline__ void warp_sort(unsigned int (&v)[R], const int lane) 
 #pragma unroll
 			for (int r = 0; r < R; r++) v[r] = upper ? __vmaxu2(v[r], q[r]) : __vminu2(v[r], q[r]);
 		}
-#pragma unroll
+#pragma unroll 1
 		for (int d = m >> 1; d >= 1; d >>= 1) {	// half-cleaners between lanes
 			const bool upper = (lane & d) != 0;
 #pragma unroll
